@@ -1,0 +1,349 @@
+/*
+ * grrt.h -- C ABI of libgrrt, the B200 (sm_100a) implementation of gr_raytracer's
+ * per-pixel geodesic-integration path.
+ *
+ * The reference (mdreem/gr_raytracer, pure Rust, CPU/rayon) has no FFI seam; the cut
+ * chosen here is the one SURVEY.md 8(b) derives from its call graph:
+ *
+ *   Raytracer::render_section_to_cie_buffer   src/rendering/raytracer.rs:177-193
+ *   Raytracer::integrate_ray_at_point         src/rendering/raytracer.rs:499-507
+ *   integrate_and_save_ray                    src/cli/shared.rs:107-129
+ *   xyz_to_linear_srgb_buffer / linear_srgb_to_srgb_buffer   src/rendering/color.rs:236-299
+ *
+ * Everything the device needs is immutable after `create_scene`
+ * (src/cli/shared.rs:131-321); it is handed over as the plain-old-data GrrtScene below.
+ * All structs are #[repr(C)]-compatible: fixed-width integers, doubles, raw pointers,
+ * no torch / C++ types.  Ownership: the caller owns every pointer it passes in (the
+ * scene is deep-copied to the device inside the call); the library owns GrrtCtx and all
+ * device memory.  Errors: integer return codes (0 = ok, <0 = GrrtStatus), no exceptions
+ * cross the boundary; per-ray failures are not API errors, they reproduce the
+ * reference's "log and keep the default pixel" (raytracer.rs:230-239) and are counted
+ * in GrrtStats.  One in-flight call per GrrtCtx.
+ */
+#ifndef GRRT_H
+#define GRRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums (values are ABI) ------------------------------------------------------ */
+
+/* configuration.rs:110-129 GeometryType */
+enum {
+    GRRT_GEOM_EUCLIDEAN = 0,
+    GRRT_GEOM_EUCLIDEAN_SPHERICAL = 1,
+    GRRT_GEOM_SCHWARZSCHILD = 2,
+    GRRT_GEOM_KERR = 3,      /* Kerr-Schild Cartesian chart, geometry/kerr.rs */
+    GRRT_GEOM_KERR_BL = 4    /* Boyer-Lindquist, Carter-separated, geometry/kerr_bl.rs */
+};
+
+/* integrator.rs:21-27 StopReason; NONE = step budget ran out without a terminal event */
+enum {
+    GRRT_STOP_NONE = 0,
+    GRRT_STOP_HORIZON = 1,
+    GRRT_STOP_CELESTIAL = 2,
+    GRRT_STOP_NAN = 3,
+    GRRT_STOP_CLOSED_ORBIT = 4,
+    GRRT_STOP_ERROR = 5      /* the ray returned Err(..): pixel keeps its default value */
+};
+
+/* scene.rs:25-30 RayClass */
+enum { GRRT_CLASS_ESCAPED = 0, GRRT_CLASS_CAPTURED = 1, GRRT_CLASS_HIT = 2 };
+
+/* per-ray error causes (the RaytracerError variants that can arise inside color_of_ray) */
+enum {
+    GRRT_RAYERR_NONE = 0,
+    GRRT_RAYERR_RKF45_RETRIES = 1,      /* runge_kutta.rs:179-181 */
+    GRRT_RAYERR_NO_CIRCULAR_ORBIT = 2,  /* circular_orbit.rs:93-101 via disc.rs:107 */
+    GRRT_RAYERR_BELOW_RISCO = 3,        /* temperature.rs:204-217 */
+    GRRT_RAYERR_NONFINITE_RADIUS = 4    /* temperature.rs:199-202 */
+};
+
+enum { GRRT_TEX_BITMAP = 0, GRRT_TEX_CHECKER = 1, GRRT_TEX_BLACKBODY = 2 };
+enum { GRRT_OBJ_SPHERE = 0, GRRT_OBJ_DISC = 1, GRRT_OBJ_VOLUMETRIC_DISC = 2 };
+enum { GRRT_TEMP_CONSTANT = 0, GRRT_TEMP_LUT = 1 };
+enum { GRRT_TONEMAP_REINHARD = 0, GRRT_TONEMAP_GLOBAL_LINEAR = 1 };
+enum { GRRT_CAMVEL_STATIC = 0, GRRT_CAMVEL_ZAMO = 1, GRRT_CAMVEL_EXPLICIT = 2 };
+
+/* Kerr-Schild right-hand-side evaluation mode (GrrtScene.kerr_rhs_mode) */
+enum {
+    GRRT_KERR_RHS_REFERENCE_FD = 0, /* central-difference metric derivative, as kerr.rs:162-186 */
+    GRRT_KERR_RHS_ANALYTIC = 1      /* closed-form derivative of f k k: faster, NOT bit-compatible */
+};
+
+typedef enum {
+    GRRT_OK = 0,
+    GRRT_ERR_INVALID_ARGUMENT = -1,
+    GRRT_ERR_INVALID_CONFIGURATION = -2,  /* RaytracerError::InvalidConfiguration */
+    GRRT_ERR_TETRAD_NOT_ORTHONORMAL = -3, /* CameraError::TetradNotOrthonormal */
+    GRRT_ERR_IO = -4,                     /* IoError / ConfigurationFileError */
+    GRRT_ERR_TOML = -5,                   /* TomlError */
+    GRRT_ERR_TEXTURE = -6,                /* TextureError */
+    GRRT_ERR_CUDA = -7,                   /* no usable device / launch failure: never a CPU fallback */
+    GRRT_ERR_OUT_OF_MEMORY = -8,
+    GRRT_ERR_LUT = -9                     /* DenominatorCloseToZero / NoCircularOrbit while building a LUT */
+} GrrtStatus;
+
+/* ---- scene description ------------------------------------------------------------ */
+
+#define GRRT_MAX_OBJECTS 8
+#define GRRT_BLACKBODY_LUT_N 1000   /* texture.rs:116 NUM_COLOR_LUT_STEPS */
+#define GRRT_TEMPERATURE_LUT_N 1000 /* temperature.rs:40 NUM_LUT_STEPS */
+
+typedef struct {
+    int32_t kind;      /* GRRT_GEOM_* */
+    int32_t _pad;
+    double radius;     /* r_s = 2M */
+    double a;          /* spin */
+    double horizon_epsilon;
+} GrrtGeometry;
+
+/* rendering/camera.rs:16-25.  position/velocity are in the geometry's native chart
+ * (spherical for Schwarzschild/EuclideanSpherical, Kerr-Schild Cartesian for Kerr,
+ * Boyer-Lindquist for KerrBL, Cartesian for Euclidean).  tetrad rows are e_t, e_x, e_y,
+ * e_z AFTER the phi/theta/psi rotations and the boost to `velocity`. */
+typedef struct {
+    double position[4];
+    double velocity[4];
+    double tetrad[4][4];
+    double alpha;              /* cli/shared.rs:162: PI/4 */
+    int64_t rows, cols;        /* rows = --height, cols = --width */
+    double spatial_signature;  /* signature[3] */
+    double spatial_handedness; /* camera.rs:134-148 */
+} GrrtCamera;
+
+/* rendering/integrator.rs:46-67 */
+typedef struct {
+    uint64_t max_steps;
+    double max_radius;
+    double step_size;
+    double epsilon;
+} GrrtIntegration;
+
+/* rendering/texture.rs: TextureMapper (bitmap) / CheckerMapper / BlackBodyMapper */
+typedef struct {
+    int32_t kind;              /* GRRT_TEX_* */
+    uint32_t width, height;    /* bitmap size in texels */
+    uint32_t _pad;
+    double beaming_exponent;
+    const uint8_t* rgba;       /* bitmap: width*height*4 bytes, row-major, 8-bit sRGB + alpha */
+    double checker_width, checker_height;
+    double c1[4], c2[4];       /* checker: CIE XYZ + alpha of color1 / color2 (srgb_to_xyz) */
+} GrrtTexture;
+
+/* rendering/temperature.rs: ConstantTemperatureComputer | KerrTemperatureComputer */
+typedef struct {
+    int32_t kind;              /* GRRT_TEMP_* */
+    uint32_t n;                /* LUT entries */
+    double constant;           /* GRRT_TEMP_CONSTANT */
+    double r_isco;             /* GRRT_TEMP_LUT: radii below this are BelowRISCO errors */
+    const double* lut_r;       /* n radii, ascending */
+    const double* lut_t;       /* n temperatures */
+} GrrtTemperature;
+
+/* scene_objects/{sphere,disc,volumetric_disc}.rs */
+typedef struct {
+    int32_t kind;              /* GRRT_OBJ_* */
+    int32_t _pad;
+    GrrtTexture texture;
+    GrrtTemperature temperature; /* Disc / VolumetricDisc */
+    /* Sphere */
+    double radius;
+    double position[3];
+    double sphere_temperature;
+    /* Disc / VolumetricDisc */
+    double inner_radius, outer_radius;
+    /* VolumetricDisc (volumetric_disc.rs:21-40) */
+    double axis[3], e1[3], e2[3];  /* normalised axis and in-plane basis (ctor :61-73) */
+    uint64_t num_octaves;
+    uint64_t vol_max_steps;
+    double vol_step_size;
+    double thickness;
+    double density_multiplier;
+    double brightness_reference_temperature;
+    double absorption, scattering;
+    double noise_scale[3];
+    double noise_offset;
+    uint8_t perlin_perm[256];      /* noise 0.9.0 PermutationTable::new(perlin_seed) */
+} GrrtObject;
+
+/* configuration.rs:21-58 AdaptiveSamplingConfig + the mask colour of cli.rs:41-47 */
+typedef struct {
+    int32_t enabled;
+    int32_t has_minimum_luminance;
+    uint64_t samples_per_axis;
+    double luminance_contrast_threshold;
+    double opacity_contrast_threshold;
+    double minimum_luminance;
+    double object_hit_opacity_threshold;
+    int32_t exclude_background_contrast;
+    int32_t show_sampling_mask;
+    double mask_xyza[4];
+} GrrtAdaptive;
+
+typedef struct {
+    GrrtGeometry geometry;
+    GrrtCamera camera;
+    GrrtIntegration integration;
+    GrrtAdaptive adaptive;
+    GrrtTexture celestial;
+    double celestial_temperature;
+    uint32_t n_objects;
+    int32_t kerr_rhs_mode;         /* GRRT_KERR_RHS_* (only read for GRRT_GEOM_KERR) */
+    GrrtObject objects[GRRT_MAX_OBJECTS];
+    /* BlackBodyMapper LUT (texture.rs:121-138), shared by every BlackBody texture */
+    uint32_t bb_lut_n;
+    uint32_t _pad;
+    const double* bb_lut_log_t;    /* bb_lut_n keys: log10(T) */
+    const double* bb_lut_xyz;      /* bb_lut_n * 3 */
+} GrrtScene;
+
+/* One stored integrator step (integrator.rs:13-19) for trajectory export. */
+typedef struct {
+    double x[4];   /* position, native chart */
+    double p[4];   /* contravariant momentum, native chart */
+    double t;      /* integration parameter (affine, or Mino time for KerrBL) */
+    uint64_t step;
+} GrrtStep;
+
+typedef struct {
+    uint64_t rays_base;            /* 1-spp rays traced */
+    uint64_t rays_supersample;     /* sub-sample rays traced */
+    uint64_t pixels_supersampled;
+    uint64_t accepted_steps;       /* sum over rays of (stored steps - 1) */
+    uint64_t attempts;             /* rkf45_step evaluations */
+    uint64_t raymarch_samples;     /* VolumetricDisc samples */
+    uint64_t stop_histogram[6];    /* indexed by GRRT_STOP_* */
+    uint64_t ray_errors;
+    uint64_t hit_stack_overflows;
+    double minimum_luminance;      /* resolved faintness floor (raytracer.rs:118-129) */
+    double device_ms_base;         /* CUDA-event time of the base pass */
+    double device_ms_mask;
+    double device_ms_supersample;
+    double device_ms_total;
+} GrrtStats;
+
+typedef struct GrrtCtx GrrtCtx;
+typedef struct GrrtDeviceScene GrrtDeviceScene;
+
+/* ---- device entry points (libgrrt.so, CUDA) ------------------------------------- */
+
+/* Create a context bound to one CUDA device.  Fails with GRRT_ERR_CUDA when there is
+ * no usable sm_100 device: there is no CPU fallback. */
+int grrt_init(int device_id, GrrtCtx** out);
+void grrt_destroy(GrrtCtx* ctx);
+const char* grrt_last_error(const GrrtCtx* ctx);
+const char* grrt_version(void);
+
+/* Drop-in for Raytracer::render_section_to_cie_buffer (raytracer.rs:177-193): base
+ * pass, adaptive mask, supersampling (or mask visualisation).  Outputs are caller-owned
+ * HOST buffers of (to_row-from_row)*(to_col-from_col) pixels, row-major; all but
+ * xyza_out may be NULL. */
+int grrt_render(GrrtCtx* ctx, const GrrtScene* scene,
+                uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
+                double* xyza_out, uint8_t* ray_class_out, uint8_t* stop_reason_out,
+                uint32_t* steps_out, GrrtStats* stats);
+
+/* xyz_to_linear_srgb_buffer + linear_srgb_to_srgb_buffer (color.rs:236-299). */
+int grrt_tonemap(GrrtCtx* ctx, const double* xyza, size_t n_pixels, int method,
+                 double exposure, uint8_t* rgb_out);
+
+/* Integrator::integrate for one ray with every stored step written out
+ * (raytracer.rs:499-507, cli/shared.rs:107-129).  pos/mom: native chart, contravariant. */
+int grrt_trace_ray(GrrtCtx* ctx, const GrrtScene* scene, const double pos[4],
+                   const double mom[4], GrrtStep* steps_out, uint64_t cap,
+                   uint64_t* n_out, int32_t* stop_reason);
+/* Same for the camera ray of pixel (row, col) (Camera::get_ray_for, camera.rs:234-245). */
+int grrt_trace_pixel_ray(GrrtCtx* ctx, const GrrtScene* scene, int64_t row, int64_t col,
+                         GrrtStep* steps_out, uint64_t cap, uint64_t* n_out,
+                         int32_t* stop_reason);
+
+/* Device-resident variants: the scene is uploaded once, inputs/outputs are DEVICE
+ * pointers and the work is enqueued on `cuda_stream` (a cudaStream_t passed as void*)
+ * without host synchronisation.  These are what bench.py's `value` and the multi-GPU
+ * tile sharding use. */
+int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* scene, GrrtDeviceScene** out);
+void grrt_scene_free(GrrtCtx* ctx, GrrtDeviceScene* dscene);
+
+/* Trace `n_items` work items.  Item i is pixel items[i] = row * cols + col of the full
+ * camera frame (items == NULL: pixel ids first_item .. first_item+n_items-1 of the
+ * rectangle [from_row,to_row) x [from_col,to_col), row-major).  samples_per_axis == 0:
+ * one centre ray per item.  samples_per_axis == N > 0: N*N stratified sub-sample rays
+ * per item (raytracer.rs:138-159) averaged over the valid ones; items whose sub-samples
+ * all failed keep xyza untouched.  Outputs are indexed by i. */
+int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* dscene,
+                            const uint32_t* d_items, uint64_t first_item, uint64_t n_items,
+                            uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
+                            uint32_t samples_per_axis,
+                            double* d_xyza, uint8_t* d_class, uint8_t* d_stop,
+                            uint32_t* d_steps, uint64_t* d_counters /* 16 u64, accumulated */,
+                            void* cuda_stream);
+
+/* resolve_minimum_luminance + collect_pixels_to_supersample (raytracer.rs:118-129,
+ * 386-458) over a complete base buffer of rows x cols pixels on the device.  Writes the
+ * flagged pixel ids (ascending, i.e. the reference's row-major push order) to
+ * d_selected and their count to *d_count. */
+int grrt_select_mask_device(GrrtCtx* ctx, const GrrtDeviceScene* dscene,
+                            const double* d_xyza, const uint8_t* d_class,
+                            uint32_t rows, uint32_t cols,
+                            uint32_t* d_selected, uint32_t* d_count,
+                            double* minimum_luminance_out, void* cuda_stream);
+
+int grrt_tonemap_device(GrrtCtx* ctx, const double* d_xyza, size_t n_pixels, int method,
+                        double exposure, uint8_t* d_rgb, void* cuda_stream);
+
+/* DFMA-chain microbenchmark: the measured FP64 issue-rate roofline denominator.
+ * Returns FP64 warp-level lane-instructions per second (one DFMA = 1). */
+int grrt_measure_fp64_peak(GrrtCtx* ctx, double* dfma_per_second, double* ms);
+
+/* ---- host-side scene assembly (mirror of src/cli + src/configuration.rs) --------- */
+
+/* cli.rs:4-48 GlobalOpts */
+typedef struct {
+    int64_t width, height;
+    double step_size;
+    uint64_t max_steps;
+    double max_radius;
+    double epsilon;
+    double camera_position[3];
+    double phi, theta, psi;
+    int32_t tone_mapping;        /* GRRT_TONEMAP_* */
+    int32_t show_sampling_mask;
+    uint8_t sampling_mask_color[3];
+    uint8_t _pad[5];
+} GrrtCliOpts;
+
+typedef struct GrrtHostScene GrrtHostScene;
+
+void grrt_cli_opts_default(GrrtCliOpts* opts);
+/* TOML file -> RenderConfig -> create_scene (cli/shared.rs:131-321) -> GrrtScene.
+ * `resource_root` (nullable) is prepended to relative texture paths. */
+int grrt_host_scene_from_toml_file(const char* toml_path, const char* resource_root,
+                                   const GrrtCliOpts* opts, GrrtHostScene** out,
+                                   char* err, size_t err_len);
+int grrt_host_scene_from_toml_string(const char* toml_text, const char* resource_root,
+                                     const GrrtCliOpts* opts, GrrtHostScene** out,
+                                     char* err, size_t err_len);
+const GrrtScene* grrt_host_scene_get(const GrrtHostScene* hs);
+void grrt_host_scene_free(GrrtHostScene* hs);
+/* render-ray-at: momentum from a Cartesian direction in the unboosted tetrad
+ * (cli/schwarzschild.rs:89-121, cli/kerr.rs:77-100, cli/kerr_bl.rs:78-107). */
+int grrt_host_ray_at(const GrrtGeometry* geometry, const double position_cartesian[3],
+                     const double direction_cartesian[3], double pos_out[4], double mom_out[4],
+                     char* err, size_t err_len);
+/* IntegratedRay::save (ray.rs:35-54): "i,t,tau,x,y,z" CSV. */
+int grrt_host_write_ray_csv(const GrrtGeometry* geometry, const GrrtStep* steps, uint64_t n,
+                            const char* path);
+int grrt_host_write_png_rgb8(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height);
+int grrt_host_write_hdr_xyz(const char* path, const double* xyza, uint32_t width, uint32_t height);
+int grrt_host_read_png_rgba8(const char* path, uint8_t** rgba_out, uint32_t* width, uint32_t* height);
+void grrt_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRRT_H */
