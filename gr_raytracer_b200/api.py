@@ -1,0 +1,248 @@
+"""ctypes binding of libgrrt.so -- the Python mirror of the reference's host-side interface.
+
+The reference is a Rust binary; its public surface for this path is the CLI (src/cli/cli.rs) and
+`Raytracer::{render_section, integrate_ray_at_point}` (src/rendering/raytracer.rs:460-507).  This
+module exposes the same operations over the C ABI of include/grrt.h.  It never falls back to a CPU
+implementation: if the CUDA library cannot be loaded or no device is present the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class GrrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"grrt error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(_HERE, "libgrrt.so")
+
+
+def lib():
+    """Load libgrrt.so (building it when missing and nvcc is available).  Fails loudly otherwise."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        from . import build as _build
+        _build.build()
+    L = C.CDLL(path)
+    vp, dp, u8p, u32p, u64p = C.c_void_p, abi.c_double_p, abi.c_uint8_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    scene_p = C.POINTER(abi.GrrtScene)
+    L.grrt_version.restype = C.c_char_p
+    L.grrt_init.argtypes = [C.c_int, C.POINTER(vp)]
+    L.grrt_destroy.argtypes = [vp]
+    L.grrt_last_error.argtypes = [vp]
+    L.grrt_last_error.restype = C.c_char_p
+    L.grrt_render.argtypes = [vp, scene_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp, u8p, u8p, u32p,
+                              C.POINTER(abi.GrrtStats)]
+    L.grrt_tonemap.argtypes = [vp, dp, C.c_size_t, C.c_int, C.c_double, u8p]
+    L.grrt_trace_ray.argtypes = [vp, scene_p, dp, dp, C.POINTER(abi.GrrtStep), C.c_uint64, u64p, C.POINTER(C.c_int32)]
+    L.grrt_trace_pixel_ray.argtypes = [vp, scene_p, C.c_int64, C.c_int64, C.POINTER(abi.GrrtStep), C.c_uint64, u64p,
+                                       C.POINTER(C.c_int32)]
+    L.grrt_scene_upload.argtypes = [vp, scene_p, C.POINTER(vp)]
+    L.grrt_scene_free.argtypes = [vp, vp]
+    L.grrt_trace_items_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp]
+    L.grrt_select_mask_device.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, dp, vp]
+    L.grrt_tonemap_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_double, vp, vp]
+    L.grrt_measure_fp64_peak.argtypes = [vp, dp, dp]
+    L.grrt_debug_pow.argtypes = [vp, dp, dp, dp, C.c_size_t]
+    for name in ("grrt_cli_opts_default", "grrt_host_scene_from_toml_file", "grrt_host_scene_from_toml_string",
+                 "grrt_host_scene_get", "grrt_host_scene_free", "grrt_host_ray_at", "grrt_host_write_ray_csv",
+                 "grrt_host_write_png_rgb8", "grrt_host_write_hdr_xyz", "grrt_host_read_png_rgba8", "grrt_host_free"):
+        if not hasattr(L, name):
+            continue
+    if hasattr(L, "grrt_host_scene_from_toml_file"):
+        L.grrt_cli_opts_default.argtypes = [C.POINTER(abi.GrrtCliOpts)]
+        L.grrt_host_scene_from_toml_file.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(abi.GrrtCliOpts), C.POINTER(vp),
+                                                     C.c_char_p, C.c_size_t]
+        L.grrt_host_scene_from_toml_string.argtypes = L.grrt_host_scene_from_toml_file.argtypes
+        L.grrt_host_scene_get.argtypes = [vp]
+        L.grrt_host_scene_get.restype = scene_p
+        L.grrt_host_scene_free.argtypes = [vp]
+        L.grrt_host_ray_at.argtypes = [C.POINTER(abi.GrrtGeometry), dp, dp, dp, dp, C.c_char_p, C.c_size_t]
+        L.grrt_host_write_ray_csv.argtypes = [C.POINTER(abi.GrrtGeometry), C.POINTER(abi.GrrtStep), C.c_uint64, C.c_char_p]
+        L.grrt_host_write_png_rgb8.argtypes = [C.c_char_p, u8p, C.c_uint32, C.c_uint32]
+        L.grrt_host_write_hdr_xyz.argtypes = [C.c_char_p, dp, C.c_uint32, C.c_uint32]
+        L.grrt_host_read_png_rgba8.argtypes = [C.c_char_p, C.POINTER(u8p), u32p, u32p]
+        L.grrt_host_free.argtypes = [vp]
+    _LIB = L
+    return L
+
+
+def _scene_ptr(scene):
+    """Accepts a HostScene, a ctypes GrrtScene, or any object with a `.c` GrrtScene (test fixtures)."""
+    if isinstance(scene, HostScene):
+        return scene.ptr
+    if isinstance(scene, abi.GrrtScene):
+        return C.byref(scene)
+    if hasattr(scene, "c"):
+        return C.byref(scene.c)
+    return scene
+
+
+def _scene_struct(scene):
+    if isinstance(scene, HostScene):
+        return scene.ptr.contents
+    if isinstance(scene, abi.GrrtScene):
+        return scene
+    return scene.c
+
+
+class HostScene:
+    """create_scene (reference src/cli/shared.rs:131-321) done by the C++ host code of libgrrt."""
+
+    def __init__(self, toml, opts=None, resource_root=None, is_text=False):
+        L = lib()
+        if not hasattr(L, "grrt_host_scene_from_toml_file"):
+            raise GrrtError(abi.ERR_INVALID_ARGUMENT, "libgrrt.so was built without the host scene code")
+        self.opts = opts or abi.default_cli_opts()
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        root = None if resource_root is None else os.fsencode(resource_root)
+        fn = L.grrt_host_scene_from_toml_string if is_text else L.grrt_host_scene_from_toml_file
+        src = toml.encode() if is_text else os.fsencode(toml)
+        rc = fn(src, root, C.byref(self.opts), C.byref(self._h), err, len(err))
+        if rc:
+            raise GrrtError(rc, err.value.decode(errors="replace"))
+        self.ptr = L.grrt_host_scene_get(self._h)
+
+    @property
+    def c(self):
+        return self.ptr.contents
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().grrt_host_scene_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GrrtCtx bound to one CUDA device."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().grrt_init(device, C.byref(self._h))
+        if rc:
+            raise GrrtError(rc, "grrt_init failed: no usable sm_100 CUDA device (this library has no CPU fallback)")
+        self.device = device
+
+    def _check(self, rc):
+        if rc < 0:
+            raise GrrtError(rc, lib().grrt_last_error(self._h).decode(errors="replace"))
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().grrt_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- Raytracer::render_section_to_cie_buffer -------------------------------------------------
+    def render(self, scene, from_row=None, from_col=None, to_row=None, to_col=None):
+        sc = _scene_struct(scene)
+        fr = 0 if from_row is None else from_row
+        fc = 0 if from_col is None else from_col
+        tr = sc.camera.rows if to_row is None else to_row
+        tc = sc.camera.cols if to_col is None else to_col
+        n = (tr - fr) * (tc - fc)
+        xyza = np.zeros((n, 4))
+        cls = np.zeros(n, dtype=np.uint8)
+        stop = np.zeros(n, dtype=np.uint8)
+        steps = np.zeros(n, dtype=np.uint32)
+        stats = abi.GrrtStats()
+        self._check(lib().grrt_render(self._h, _scene_ptr(scene), fr, fc, tr, tc,
+                                      xyza.ctypes.data_as(abi.c_double_p), cls.ctypes.data_as(abi.c_uint8_p),
+                                      stop.ctypes.data_as(abi.c_uint8_p), steps.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                      C.byref(stats)))
+        shape = (tr - fr, tc - fc)
+        return dict(xyza=xyza.reshape(shape + (4,)), ray_class=cls.reshape(shape), stop=stop.reshape(shape),
+                    steps=steps.reshape(shape), stats=stats.as_dict())
+
+    def tonemap(self, xyza, method=abi.TONEMAP_REINHARD, exposure=1.0):
+        a = np.ascontiguousarray(xyza, dtype=np.float64).reshape(-1, 4)
+        rgb = np.zeros((a.shape[0], 3), dtype=np.uint8)
+        self._check(lib().grrt_tonemap(self._h, a.ctypes.data_as(abi.c_double_p), a.shape[0], method, exposure,
+                                       rgb.ctypes.data_as(abi.c_uint8_p)))
+        return rgb.reshape(np.shape(xyza)[:-1] + (3,))
+
+    # -- Integrator::integrate with stored steps (render-ray / render-ray-at) -------------------------
+    def trace_ray(self, scene, pos=None, mom=None, pixel=None, cap=None):
+        sc = _scene_struct(scene)
+        cap = int(cap or sc.integration.max_steps)
+        buf = (abi.GrrtStep * cap)()
+        n, stop = C.c_uint64(), C.c_int32()
+        if pixel is not None:
+            err = self._check(lib().grrt_trace_pixel_ray(self._h, _scene_ptr(scene), pixel[0], pixel[1], buf, cap,
+                                                         C.byref(n), C.byref(stop)))
+        else:
+            p = (C.c_double * 4)(*pos)
+            m = (C.c_double * 4)(*mom)
+            err = self._check(lib().grrt_trace_ray(self._h, _scene_ptr(scene), p, m, buf, cap, C.byref(n), C.byref(stop)))
+        m_ = min(n.value, cap)
+        dt = np.dtype([("x", "f8", 4), ("p", "f8", 4), ("t", "f8"), ("step", "u8")])
+        return np.frombuffer(buf, dtype=dt, count=m_).copy(), stop.value, err
+
+    def debug_pow(self, x, y):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(np.broadcast_to(y, x.shape), dtype=np.float64)
+        out = np.zeros_like(x)
+        self._check(lib().grrt_debug_pow(self._h, x.ctypes.data_as(abi.c_double_p), y.ctypes.data_as(abi.c_double_p),
+                                         out.ctypes.data_as(abi.c_double_p), x.size))
+        return out
+
+    def measure_fp64_peak(self):
+        rate, ms = C.c_double(), C.c_double()
+        self._check(lib().grrt_measure_fp64_peak(self._h, C.byref(rate), C.byref(ms)))
+        return rate.value, ms.value
+
+    # -- device-resident API (bench / multi-GPU) --------------------------------------------------------
+    def upload(self, scene):
+        h = C.c_void_p()
+        self._check(lib().grrt_scene_upload(self._h, _scene_ptr(scene), C.byref(h)))
+        return h
+
+    def free_scene(self, h):
+        lib().grrt_scene_free(self._h, h)
+
+    def trace_items_device(self, dscene, d_items, first_item, n_items, rect, spa, d_xyza, d_class=None, d_stop=None,
+                           d_steps=None, d_counters=None, stream=None):
+        fr, fc, tr, tc = rect
+        return self._check(lib().grrt_trace_items_device(self._h, dscene, d_items, first_item, n_items, fr, fc, tr, tc,
+                                                         spa, d_xyza, d_class, d_stop, d_steps, d_counters, stream))
+
+    def select_mask_device(self, dscene, d_xyza, d_class, rows, cols, d_selected, d_count, stream=None):
+        ml = C.c_double()
+        self._check(lib().grrt_select_mask_device(self._h, dscene, d_xyza, d_class, rows, cols, d_selected, d_count,
+                                                  C.byref(ml), stream))
+        return ml.value
+
+    def tonemap_device(self, d_xyza, n, method, exposure, d_rgb, stream=None):
+        return self._check(lib().grrt_tonemap_device(self._h, d_xyza, n, method, exposure, d_rgb, stream))

@@ -1,0 +1,846 @@
+// grrt_api.cu -- device half of the C ABI declared in include/grrt.h.
+//
+// Compiled for sm_100a only (-gencode arch=compute_100a,code=sm_100a -fmad=false).  There is no CPU
+// path in this library: every entry point that computes needs a CUDA device and fails with
+// GRRT_ERR_CUDA otherwise.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "grrt_trace.cuh"
+
+using namespace grrt;
+
+struct GrrtCtx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    double* d_srgb_lut = nullptr;
+    unsigned long long* d_queue = nullptr;     // work-queue counter
+    unsigned long long* d_counters = nullptr;  // 16 x u64
+    void* d_cub_temp = nullptr;
+    size_t cub_temp_bytes = 0;
+};
+
+struct GrrtDeviceScene {
+    DScene s;
+    std::vector<void*> allocs;
+    GrrtAdaptive adaptive;
+    bool has_vol = false;
+};
+
+namespace {
+
+#define CUDA_TRY(ctx, expr)                                                                     \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);             \
+            return _e == cudaErrorMemoryAllocation ? GRRT_ERR_OUT_OF_MEMORY : GRRT_ERR_CUDA;    \
+        }                                                                                       \
+    } while (0)
+
+int fail(GrrtCtx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+double inv_compand_srgb_host(double u) {  // color.rs:301-308 (glibc pow, as the reference)
+    if (u <= 0.04045) return u / 12.92;
+    return std::pow((u + 0.055) / 1.055, 2.4);
+}
+
+template <class T>
+int upload(GrrtCtx* ctx, GrrtDeviceScene* ds, const T* host, size_t count, const T** out) {
+    *out = nullptr;
+    if (!host || count == 0) return GRRT_OK;
+    void* p = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&p, count * sizeof(T)));
+    ds->allocs.push_back(p);
+    CUDA_TRY(ctx, cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = static_cast<const T*>(p);
+    return GRRT_OK;
+}
+
+int convert_texture(GrrtCtx* ctx, GrrtDeviceScene* ds, const GrrtTexture& t, DTexture* o,
+                    std::map<const uint8_t*, const uint8_t*>& cache) {
+    std::memset(o, 0, sizeof *o);
+    o->kind = t.kind;
+    o->width = t.width;
+    o->height = t.height;
+    o->beaming = t.beaming_exponent;
+    o->cw = t.checker_width;
+    o->ch = t.checker_height;
+    for (int i = 0; i < 4; ++i) {
+        o->c1[i] = t.c1[i];
+        o->c2[i] = t.c2[i];
+    }
+    if (t.kind == GRRT_TEX_BITMAP) {
+        if (!t.rgba || t.width == 0 || t.height == 0) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "bitmap texture without pixels");
+        auto it = cache.find(t.rgba);
+        if (it == cache.end()) {
+            const uint8_t* d = nullptr;
+            int rc = upload<uint8_t>(ctx, ds, t.rgba, (size_t)t.width * t.height * 4, &d);
+            if (rc) return rc;
+            it = cache.emplace(t.rgba, d).first;
+        }
+        o->rgba = it->second;
+    }
+    return GRRT_OK;
+}
+
+// ---- adaptive-sampling mask (raytracer.rs:59-129, 386-458) ------------------------------------------
+__global__ void luminance_keys_kernel(const double* xyza, size_t n, unsigned long long* keys) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long b = __double_as_longlong(xyza[4 * i + 1]);
+    // f64::total_cmp order as an unsigned key
+    unsigned long long u = (unsigned long long)b;
+    u = (b < 0) ? ~u : (u | 0x8000000000000000ull);
+    keys[i] = u;
+}
+__device__ __forceinline__ bool should_supersample_pair(const double* p, int pc, const double* q, int qc,
+                                                        const GrrtAdaptive& cfg, double minimum_luminance) {
+    if (pc != qc) return true;
+    if (cfg.exclude_background_contrast && pc == GRRT_CLASS_ESCAPED) return false;
+    bool visible = fmax(p[1], q[1]) > minimum_luminance;
+    double lc = fabs(p[1] - q[1]) / (p[1] + q[1] + 1e-4);
+    double oc = fabs(p[3] - q[3]);
+    return visible && (lc > cfg.luminance_contrast_threshold || oc > cfg.opacity_contrast_threshold);
+}
+__global__ void mask_flags_kernel(const double* xyza, const uint8_t* cls, uint32_t H, uint32_t W,
+                                  const __grid_constant__ GrrtAdaptive cfg, const unsigned long long* key_at_index,
+                                  double* min_lum_out, uint8_t* flags) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    double min_lum;
+    if (cfg.has_minimum_luminance) {
+        min_lum = cfg.minimum_luminance;
+    } else {
+        unsigned long long u = *key_at_index;
+        long long b = (u & 0x8000000000000000ull) ? (long long)(u & 0x7fffffffffffffffull) : (long long)~u;
+        min_lum = 1e-3 * __longlong_as_double(b);  // RELATIVE_MINIMUM_LUMINANCE_FRACTION
+    }
+    if (i == 0) *min_lum_out = min_lum;
+    if (i >= (size_t)H * W) return;
+    int row = (int)(i / W), col = (int)(i % W);
+    const double* p = xyza + 4 * i;
+    int pc = cls[i];
+    bool flag = false;
+    const int SH[8][2] = {{-1, -1}, {-1, 0}, {-1, 1}, {0, -1}, {0, 1}, {1, -1}, {1, 0}, {1, 1}};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int nr = row + SH[k][0], nc = col + SH[k][1];
+        if (nr < 0 || nr >= (int)H || nc < 0 || nc >= (int)W) continue;
+        size_t ni = (size_t)nr * W + nc;
+        if (should_supersample_pair(p, pc, xyza + 4 * ni, cls[ni], cfg, min_lum)) {
+            flag = true;
+            break;
+        }
+    }
+    flags[i] = flag ? 1 : 0;
+}
+__global__ void fill_mask_color_kernel(const uint32_t* sel, uint32_t n, const __grid_constant__ GrrtAdaptive cfg, double* xyza) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* d = xyza + 4ull * sel[i];
+    d[0] = cfg.mask_xyza[0]; d[1] = cfg.mask_xyza[1]; d[2] = cfg.mask_xyza[2]; d[3] = cfg.mask_xyza[3];
+}
+
+// ---- tone mapping (color.rs:193-299) ----------------------------------------------------------------
+__device__ __forceinline__ void xyz_to_linear(const double* c, double out[3]) {
+    out[0] = (3.2406255 * c[0] + -1.5372080 * c[1]) + -0.4986286 * c[2];
+    out[1] = (-0.9689307 * c[0] + 1.8757561 * c[1]) + 0.0415175 * c[2];
+    out[2] = (0.0557101 * c[0] + -0.2040211 * c[1]) + 1.0569959 * c[2];
+}
+__device__ __forceinline__ double compand_srgb(double linear) {
+    double sign = linear < 0.0 ? -1.0 : 1.0;
+    double a = fabs(linear);
+    double enc = (a <= 0.0031308) ? 12.92 * a : 1.055 * pow(a, 1.0 / 2.4) - 0.055;
+    return rclamp(sign * enc, 0.0, 1.0);
+}
+__device__ __forceinline__ uint8_t to_u8(double v) {
+    double r = round(v);
+    if (!(r > 0.0)) return 0;
+    if (r >= 255.0) return 255;
+    return (uint8_t)r;
+}
+struct FMaxOp {
+    __device__ __forceinline__ double operator()(double a, double b) const { return fmax(a, b); }
+};
+__global__ void linear_max_kernel(const double* xyza, size_t n, double exposure, double* comp_max) {
+    // max over pixels of lin*exposure for r,g,b: fold(0.0, f64::max); block reduce + atomic on the ordered bits
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    double m = 0.0;
+    if (i < n) {
+        double lin[3];
+        xyz_to_linear(xyza + 4 * i, lin);
+        m = fmax(fmax(fmax(0.0, lin[0] * exposure), lin[1] * exposure), lin[2] * exposure);
+    }
+    typedef cub::BlockReduce<double, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    double bm = BR(tmp).Reduce(m, FMaxOp());
+    if (threadIdx.x == 0 && bm > 0.0)  // non-negative doubles order like their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long*>(comp_max), (unsigned long long)__double_as_longlong(bm));
+}
+__global__ void tonemap_kernel(const double* xyza, size_t n, int method, double exposure, const double* comp_max,
+                               uint8_t* rgb) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double c[3];
+    xyz_to_linear(xyza + 4 * i, c);
+    c[0] *= exposure; c[1] *= exposure; c[2] *= exposure;
+    if (method == GRRT_TONEMAP_REINHARD) {
+        double l_in = (0.2126 * c[0] + 0.7152 * c[1]) + 0.0722 * c[2];
+        if (l_in > 0.0) {
+            double l_out = l_in / (1.0 + l_in);
+            double f = l_out / l_in;
+            c[0] *= f; c[1] *= f; c[2] *= f;
+        }
+    } else {
+        double mc = *comp_max;
+        double scale = mc > 0.0 ? 1.0 / mc : 1.0;
+        c[0] = scale * c[0]; c[1] = scale * c[1]; c[2] = scale * c[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rgb[3 * i + k] = to_u8(compand_srgb(fmax(c[k], 0.0)) * 255.0);
+}
+
+// ---- single-ray trajectory export (integrator.rs:78-174 with every step stored) ---------------------
+template <int G>
+__global__ void trace_single_kernel(const __grid_constant__ DScene S, const double4 pos4, const double4 mom4,
+                                    int use_pixel, long long row, long long col, GrrtStep* steps,
+                                    unsigned long long cap, unsigned long long* n_out, int* stop_out, int* err_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double pos[4] = {pos4.x, pos4.y, pos4.z, pos4.w}, mom[4] = {mom4.x, mom4.y, mom4.z, mom4.w};
+    if (use_pixel) camera_ray<G>(S, (double)row, (double)col, pos, mom);
+    double y[8];
+    RayConst C;
+    RayCtx R;
+    init_ray<G>(S, pos, mom, y, C, R);
+    unsigned long long n = 0;
+    double t = 0.0;
+    auto store = [&](unsigned long long step) {
+        if (n < cap) {
+            double p[4];
+            momentum_from_state<G>(S, C, y, p);
+            for (int i = 0; i < 4; ++i) {
+                steps[n].x[i] = y[i];
+                steps[n].p[i] = p[i];
+            }
+            steps[n].t = t;
+            steps[n].step = step;
+        }
+        ++n;
+    };
+    store(0);
+    double h = S.step_size;
+    int stop = GRRT_STOP_NONE, error = 0;
+    for (unsigned long long i = 1; i < S.max_steps && !error; ++i) {
+        double h_cur = rclamp(h, kHMin, kHMax);
+        bool ok = false;
+        double y_new[8], err;
+        for (int r = 0; r < kMaxRetryStep; ++r) {
+            rkf45_step<G>(S, C, y, h_cur, y_new, err);
+            double h_proposed = err > 0.0 ? 0.9 * h_cur * pow_glibc(pow_tables_global(), S.epsilon / err, 1.0 / 5.0) : h_cur * kHGrowthCap;
+            h_proposed = rclamp(fmin(h_proposed, h_cur * kHGrowthCap), kHMin, kHMax);
+            if (err > S.epsilon) {
+                if (h_cur <= kHMin) {
+                    h = h_cur;
+                    ok = true;
+                    break;
+                }
+                h_cur = rclamp(h_proposed / 2.0, kHMin, kHMax);
+            } else {
+                h = (err / S.epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
+                ok = true;
+                break;
+            }
+        }
+        if (!ok) {
+            error = GRRT_RAYERR_RKF45_RETRIES;
+            stop = GRRT_STOP_ERROR;
+            break;
+        }
+        for (int k = 0; k < 8; ++k) y[k] = y_new[k];
+        t += h_cur;
+        store(i);
+        stop = should_stop<G>(S, y, position_cartesian<G>(S, y), i);
+        if (stop != GRRT_STOP_NONE) break;
+    }
+    *n_out = n;
+    *stop_out = stop;
+    *err_out = error;
+}
+
+// ---- FP64 issue-rate microbenchmark -----------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0,
+           x7 = x0 + 7.0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+__global__ void debug_pow_kernel(const double* x, const double* y, double* out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pow_glibc(pow_tables_global(), x[i], y[i]);
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------------
+template <int G, bool V>
+int launch_trace_t(GrrtCtx* ctx, const DScene& s, const TraceArgs& a, cudaStream_t st) {
+    int per_sm = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<G, V>, kTraceThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long want = (a.n_units + kTraceThreads - 1) / kTraceThreads;
+    unsigned long long grid = (unsigned long long)ctx->num_sms * per_sm;  // persistent: one wave, a multiple of the SM count
+    if (want < grid) grid = want;
+    if (grid == 0) return GRRT_OK;
+    trace_kernel<G, V><<<(unsigned)grid, kTraceThreads, 0, st>>>(s, a);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return GRRT_OK;
+}
+template <bool V>
+int launch_trace_v(GrrtCtx* ctx, const DScene& s, const TraceArgs& a, cudaStream_t st) {
+    switch (s.geom) {
+        case GRRT_GEOM_EUCLIDEAN: return launch_trace_t<GRRT_GEOM_EUCLIDEAN, V>(ctx, s, a, st);
+        case GRRT_GEOM_EUCLIDEAN_SPHERICAL: return launch_trace_t<GRRT_GEOM_EUCLIDEAN_SPHERICAL, V>(ctx, s, a, st);
+        case GRRT_GEOM_SCHWARZSCHILD: return launch_trace_t<GRRT_GEOM_SCHWARZSCHILD, V>(ctx, s, a, st);
+        case GRRT_GEOM_KERR: return launch_trace_t<GRRT_GEOM_KERR, V>(ctx, s, a, st);
+        case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V>(ctx, s, a, st);
+        default: return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "unknown geometry kind");
+    }
+}
+int launch_trace(GrrtCtx* ctx, const GrrtDeviceScene* ds, const TraceArgs& a, cudaStream_t st) {
+    return ds->has_vol ? launch_trace_v<true>(ctx, ds->s, a, st) : launch_trace_v<false>(ctx, ds->s, a, st);
+}
+
+int ensure_cub_temp(GrrtCtx* ctx, size_t bytes) {
+    if (bytes <= ctx->cub_temp_bytes) return GRRT_OK;
+    if (ctx->d_cub_temp) cudaFree(ctx->d_cub_temp);
+    ctx->d_cub_temp = nullptr;
+    ctx->cub_temp_bytes = 0;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_cub_temp, bytes));
+    ctx->cub_temp_bytes = bytes;
+    return GRRT_OK;
+}
+
+struct DevBuf {  // RAII device allocation
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+const char* grrt_version(void) { return "grrt-b200 0.1 (sm_100a)"; }
+
+int grrt_init(int device_id, GrrtCtx** out) {
+    if (!out) return GRRT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device_id < 0 || device_id >= count) return GRRT_ERR_CUDA;
+    GrrtCtx* ctx = new GrrtCtx();
+    ctx->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return GRRT_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { delete ctx; return GRRT_ERR_CUDA; }
+    if (prop.major < 10) {  // the only code in this library is sm_100a SASS
+        delete ctx;
+        return GRRT_ERR_CUDA;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GRRT_ERR_CUDA; }
+    double lut[256];
+    for (int i = 0; i < 256; ++i) lut[i] = inv_compand_srgb_host((double)i / 255.0);
+    if (cudaMalloc(&ctx->d_srgb_lut, sizeof lut) != cudaSuccess ||
+        cudaMemcpy(ctx->d_srgb_lut, lut, sizeof lut, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMalloc(&ctx->d_queue, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) {
+        grrt_destroy(ctx);
+        return GRRT_ERR_CUDA;
+    }
+    *out = ctx;
+    return GRRT_OK;
+}
+
+void grrt_destroy(GrrtCtx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_srgb_lut) cudaFree(ctx->d_srgb_lut);
+    if (ctx->d_queue) cudaFree(ctx->d_queue);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_cub_temp) cudaFree(ctx->d_cub_temp);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* grrt_last_error(const GrrtCtx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
+
+int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) {
+    if (!ctx || !sc || !out) return GRRT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (sc->n_objects > GRRT_MAX_OBJECTS) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "too many objects");
+    if (sc->camera.rows <= 0 || sc->camera.cols <= 0) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "camera has no pixels");
+    GrrtDeviceScene* ds = new GrrtDeviceScene();
+    auto bail = [&](int rc) {
+        grrt_scene_free(ctx, ds);
+        return rc;
+    };
+    DScene& s = ds->s;
+    std::memset(&s, 0, sizeof s);
+    ds->adaptive = sc->adaptive;
+    s.geom = sc->geometry.kind;
+    s.kerr_mode = sc->kerr_rhs_mode;
+    s.radius = sc->geometry.radius;
+    s.a = sc->geometry.a;
+    s.heps = sc->geometry.horizon_epsilon;
+    {  // kerr.rs:382-394 / kerr_bl.rs:482-492
+        double m = (s.geom == GRRT_GEOM_KERR) ? 0.5 * s.radius : s.radius / 2.0;
+        s.horizon_enabled = !(std::fabs(s.a) > s.radius / 2.0);
+        double disc = std::fmax(m * m - s.a * s.a, 0.0);
+        double rp = m + std::sqrt(disc);
+        s.r_plus_eps = rp + s.heps;
+    }
+    s.n_objects = (int)sc->n_objects;
+    for (int i = 0; i < 4; ++i) {
+        s.cam_pos[i] = sc->camera.position[i];
+        s.cam_vel[i] = sc->camera.velocity[i];
+        for (int j = 0; j < 4; ++j) s.tet[i][j] = sc->camera.tetrad[i][j];
+    }
+    s.cam_rows = (double)sc->camera.rows;
+    s.cam_cols = (double)sc->camera.cols;
+    s.cam_scale = 2.0 * std::tan(sc->camera.alpha / 2.0) / (double)sc->camera.rows;  // camera.rs:217-224
+    s.cam_hand = sc->camera.spatial_handedness;
+    s.cam_sig = sc->camera.spatial_signature;
+    s.max_steps = sc->integration.max_steps;
+    s.max_radius_sq = sc->integration.max_radius * sc->integration.max_radius;  // integrator.rs:62
+    s.step_size = sc->integration.step_size;
+    s.epsilon = sc->integration.epsilon;
+    s.hit_opacity_threshold = sc->adaptive.object_hit_opacity_threshold;
+    s.celestial_temperature = sc->celestial_temperature;
+    s.srgb_lut = ctx->d_srgb_lut;
+    std::map<const uint8_t*, const uint8_t*> tex_cache;
+    int rc = convert_texture(ctx, ds, sc->celestial, &s.celestial, tex_cache);
+    if (rc) return bail(rc);
+    bool need_bb = sc->celestial.kind == GRRT_TEX_BLACKBODY;
+    int n_vol = 0;
+    for (uint32_t k = 0; k < sc->n_objects; ++k) {
+        const GrrtObject& o = sc->objects[k];
+        DObject& d = s.obj[k];
+        d.kind = o.kind;
+        rc = convert_texture(ctx, ds, o.texture, &d.tex, tex_cache);
+        if (rc) return bail(rc);
+        need_bb = need_bb || o.texture.kind == GRRT_TEX_BLACKBODY;
+        d.temp.kind = o.temperature.kind;
+        d.temp.n = o.temperature.n;
+        d.temp.constant = o.temperature.constant;
+        d.temp.r_isco = o.temperature.r_isco;
+        if (o.kind != GRRT_OBJ_SPHERE && o.temperature.kind == GRRT_TEMP_LUT) {
+            if ((rc = upload<double>(ctx, ds, o.temperature.lut_r, o.temperature.n, &d.temp.lut_r))) return bail(rc);
+            if ((rc = upload<double>(ctx, ds, o.temperature.lut_t, o.temperature.n, &d.temp.lut_t))) return bail(rc);
+        }
+        d.radius = o.radius;
+        d.sphere_temperature = o.sphere_temperature;
+        d.r_in = o.inner_radius;
+        d.r_out = o.outer_radius;
+        for (int i = 0; i < 3; ++i) {
+            d.pos[i] = o.position[i];
+            d.axis[i] = o.axis[i];
+            d.e1[i] = o.e1[i];
+            d.e2[i] = o.e2[i];
+            d.noise_scale[i] = o.noise_scale[i];
+        }
+        d.num_octaves = o.num_octaves;
+        d.vol_max_steps = o.vol_max_steps;
+        d.vol_step = o.vol_step_size;
+        d.thickness = o.thickness;
+        d.density_multiplier = o.density_multiplier;
+        d.bref_temperature = o.brightness_reference_temperature;
+        d.absorption = o.absorption;
+        d.scattering = o.scattering;
+        d.noise_offset = o.noise_offset;
+        if (o.kind == GRRT_OBJ_VOLUMETRIC_DISC) {
+            d.perm_slot = n_vol++;
+            if ((rc = upload<uint8_t>(ctx, ds, o.perlin_perm, 256, &d.perm))) return bail(rc);
+        }
+    }
+    s.n_vol = (uint32_t)n_vol;
+    ds->has_vol = n_vol > 0;
+    if (need_bb) {
+        if (!sc->bb_lut_log_t || !sc->bb_lut_xyz || sc->bb_lut_n == 0)
+            return bail(fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "BlackBody texture without a black-body LUT"));
+        s.bb_n = sc->bb_lut_n;
+        if ((rc = upload<double>(ctx, ds, sc->bb_lut_log_t, sc->bb_lut_n, &s.bb_log_t))) return bail(rc);
+        if ((rc = upload<double>(ctx, ds, sc->bb_lut_xyz, (size_t)sc->bb_lut_n * 3, &s.bb_xyz))) return bail(rc);
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = ds;
+    return GRRT_OK;
+}
+
+void grrt_scene_free(GrrtCtx* ctx, GrrtDeviceScene* ds) {
+    if (!ds) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    for (void* p : ds->allocs) cudaFree(p);
+    delete ds;
+}
+
+int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_items, uint64_t first_item,
+                            uint64_t n_items, uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
+                            uint32_t samples_per_axis, double* d_xyza, uint8_t* d_class, uint8_t* d_stop,
+                            uint32_t* d_steps, uint64_t* d_counters, void* cuda_stream) {
+    if (!ctx || !ds || !d_xyza) return GRRT_ERR_INVALID_ARGUMENT;
+    if (to_row < from_row || to_col < from_col) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "empty or inverted section");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (n_items == 0) return GRRT_OK;
+    TraceArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.items = d_items;
+    a.first_item = first_item;
+    a.n_items = n_items;
+    a.from_row = from_row;
+    a.from_col = from_col;
+    a.width = to_col - from_col;
+    a.height = to_row - from_row;
+    a.queue = ctx->d_queue;
+    a.counters = (unsigned long long*)d_counters;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned long long), st));
+    if (samples_per_axis == 0) {
+        a.spa = 0;
+        a.xyza = d_xyza;
+        a.cls = d_class;
+        a.stop = d_stop;
+        a.steps = d_steps;
+        const bool whole = !d_items && first_item == 0 && n_items == (uint64_t)a.width * a.height;
+        if (whole) {  // enumerate 8x4 pixel tiles so that a warp starts on a compact patch of the image
+            a.tiled = 1;
+            a.tiles_x = (a.width + 7) / 8;
+            a.n_units = (unsigned long long)a.tiles_x * ((a.height + 3) / 4) * 32ull;
+        } else {
+            a.n_units = n_items;
+        }
+        return launch_trace(ctx, ds, a, st);
+    }
+    if (!d_items) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "sub-sample mode needs an explicit item list");
+    // sub-sample mode: trace N*N rays per item into scratch, then average in stratum order
+    const unsigned ss = samples_per_axis * samples_per_axis;
+    const uint64_t chunk_items = std::max<uint64_t>(1, (uint64_t)(1ull << 28) / ss);  // <= 8 GiB of scratch
+    DevBuf sub, valid;
+    const uint64_t cap = std::min<uint64_t>(chunk_items, n_items);
+    CUDA_TRY(ctx, sub.alloc(cap * ss * 4 * sizeof(double)));
+    CUDA_TRY(ctx, valid.alloc(cap * ss));
+    for (uint64_t off = 0; off < n_items; off += cap) {
+        uint64_t m = std::min<uint64_t>(cap, n_items - off);
+        a.items = d_items + off;
+        a.n_items = m;
+        a.spa = samples_per_axis;
+        a.n_units = m * ss;
+        a.xyza = sub.as<double>();
+        a.sub_valid = valid.as<uint8_t>();
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned long long), st));
+        int rc = launch_trace(ctx, ds, a, st);
+        if (rc) return rc;
+        resolve_subsamples_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(sub.as<double>(), valid.as<uint8_t>(),
+                                                                                d_items + off, m, ss, d_xyza);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));  // scratch is freed on return
+    return GRRT_OK;
+}
+
+int grrt_select_mask_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const double* d_xyza, const uint8_t* d_class,
+                            uint32_t rows, uint32_t cols, uint32_t* d_selected, uint32_t* d_count,
+                            double* minimum_luminance_out, void* cuda_stream) {
+    if (!ctx || !ds || !d_xyza || !d_class || !d_selected || !d_count) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const size_t n = (size_t)rows * cols;
+    if (n == 0) {
+        CUDA_TRY(ctx, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), st));
+        if (minimum_luminance_out) *minimum_luminance_out = 0.0;
+        return GRRT_OK;
+    }
+    DevBuf keys_in, keys_out, flags, minlum;
+    CUDA_TRY(ctx, flags.alloc(n));
+    CUDA_TRY(ctx, minlum.alloc(sizeof(double)));
+    const unsigned long long* key_at = nullptr;
+    if (!ds->adaptive.has_minimum_luminance) {  // 99th percentile by a full radix sort of total_cmp keys
+        CUDA_TRY(ctx, keys_in.alloc(n * 8));
+        CUDA_TRY(ctx, keys_out.alloc(n * 8));
+        luminance_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyza, n, keys_in.as<unsigned long long>());
+        size_t tmp = 0;
+        CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys_in.as<unsigned long long>(),
+                                                     keys_out.as<unsigned long long>(), (long long)n, 0, 64, st));
+        int rc = ensure_cub_temp(ctx, tmp);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(ctx->d_cub_temp, tmp, keys_in.as<unsigned long long>(),
+                                                     keys_out.as<unsigned long long>(), (long long)n, 0, 64, st));
+        size_t index = (size_t)((double)(n - 1) * 0.99);  // raytracer.rs:126
+        key_at = keys_out.as<unsigned long long>() + index;
+    }
+    mask_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyza, d_class, rows, cols, ds->adaptive, key_at,
+                                                                    minlum.as<double>(), flags.as<uint8_t>());
+    CUDA_TRY(ctx, cudaGetLastError());
+    {
+        cub::CountingInputIterator<uint32_t> ids(0);
+        size_t tmp = 0;
+        CUDA_TRY(ctx, cub::DeviceSelect::Flagged(nullptr, tmp, ids, flags.as<uint8_t>(), d_selected, d_count, (long long)n, st));
+        int rc = ensure_cub_temp(ctx, tmp);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cub::DeviceSelect::Flagged(ctx->d_cub_temp, tmp, ids, flags.as<uint8_t>(), d_selected, d_count,
+                                                 (long long)n, st));
+    }
+    double ml = 0.0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&ml, minlum.p, sizeof ml, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (minimum_luminance_out) *minimum_luminance_out = ml;
+    return GRRT_OK;
+}
+
+int grrt_tonemap_device(GrrtCtx* ctx, const double* d_xyza, size_t n, int method, double exposure, uint8_t* d_rgb,
+                        void* cuda_stream) {
+    if (!ctx || !d_xyza || !d_rgb) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (n == 0) return GRRT_OK;
+    double* d_max = reinterpret_cast<double*>(ctx->d_counters + 15);
+    if (method == GRRT_TONEMAP_GLOBAL_LINEAR) {
+        CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, sizeof(double), st));
+        linear_max_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyza, n, exposure, d_max);
+    }
+    tonemap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyza, n, method, exposure, d_max, d_rgb);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return GRRT_OK;
+}
+
+int grrt_tonemap(GrrtCtx* ctx, const double* xyza, size_t n, int method, double exposure, uint8_t* rgb_out) {
+    if (!ctx || !xyza || !rgb_out) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf in, out;
+    CUDA_TRY(ctx, in.alloc(n * 32));
+    CUDA_TRY(ctx, out.alloc(n * 3));
+    CUDA_TRY(ctx, cudaMemcpyAsync(in.p, xyza, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = grrt_tonemap_device(ctx, in.as<double>(), n, method, exposure, out.as<uint8_t>(), ctx->stream);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(rgb_out, out.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRRT_OK;
+}
+
+int grrt_render(GrrtCtx* ctx, const GrrtScene* scene, uint32_t from_row, uint32_t from_col, uint32_t to_row,
+                uint32_t to_col, double* xyza_out, uint8_t* ray_class_out, uint8_t* stop_reason_out, uint32_t* steps_out,
+                GrrtStats* stats) {
+    if (!ctx || !scene || !xyza_out) return GRRT_ERR_INVALID_ARGUMENT;
+    if (to_row < from_row || to_col < from_col) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "inverted section");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GrrtDeviceScene* ds = nullptr;
+    int rc = grrt_scene_upload(ctx, scene, &ds);
+    if (rc) return rc;
+    struct Guard {
+        GrrtCtx* c;
+        GrrtDeviceScene* d;
+        ~Guard() { grrt_scene_free(c, d); }
+    } guard{ctx, ds};
+    const uint32_t W = to_col - from_col, H = to_row - from_row;
+    const size_t n = (size_t)W * H;
+    GrrtStats st;
+    std::memset(&st, 0, sizeof st);
+    if (n == 0) {
+        if (stats) *stats = st;
+        return GRRT_OK;
+    }
+    cudaStream_t s = ctx->stream;
+    DevBuf xyza, cls, stop, steps, sel, cnt;
+    CUDA_TRY(ctx, xyza.alloc(n * 32));
+    CUDA_TRY(ctx, cls.alloc(n));
+    CUDA_TRY(ctx, stop.alloc(n));
+    CUDA_TRY(ctx, steps.alloc(n * 4));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), s));
+    cudaEvent_t ev[4];
+    for (auto& e : ev) CUDA_TRY(ctx, cudaEventCreate(&e));
+    struct EvGuard {
+        cudaEvent_t* e;
+        ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); }
+    } evg{ev};
+    CUDA_TRY(ctx, cudaEventRecord(ev[0], s));
+    rc = grrt_trace_items_device(ctx, ds, nullptr, 0, n, from_row, from_col, to_row, to_col, 0, xyza.as<double>(),
+                                 cls.as<uint8_t>(), stop.as<uint8_t>(), steps.as<uint32_t>(),
+                                 (uint64_t*)ctx->d_counters, s);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ev[1], s));
+    st.rays_base = n;
+    const GrrtAdaptive& ad = scene->adaptive;
+    uint32_t n_sel = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ev[2], s));
+    if (ad.enabled || ad.show_sampling_mask) {  // raytracer.rs:184
+        CUDA_TRY(ctx, sel.alloc(n * 4));
+        CUDA_TRY(ctx, cnt.alloc(4));
+        rc = grrt_select_mask_device(ctx, ds, xyza.as<double>(), cls.as<uint8_t>(), H, W, sel.as<uint32_t>(),
+                                     cnt.as<uint32_t>(), &st.minimum_luminance, s);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaMemcpy(&n_sel, cnt.p, 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaEventRecord(ev[2], s));
+        st.pixels_supersampled = n_sel;
+        if (n_sel) {
+            if (ad.show_sampling_mask) {
+                fill_mask_color_kernel<<<(n_sel + 255) / 256, 256, 0, s>>>(sel.as<uint32_t>(), n_sel, ad, xyza.as<double>());
+                CUDA_TRY(ctx, cudaGetLastError());
+            } else {
+                if (ad.samples_per_axis == 0 || ad.samples_per_axis > 4096)
+                    return fail(ctx, GRRT_ERR_INVALID_CONFIGURATION, "adaptive_sampling.samples_per_axis must be greater than zero");
+                rc = grrt_trace_items_device(ctx, ds, sel.as<uint32_t>(), 0, n_sel, from_row, from_col, to_row, to_col,
+                                             (uint32_t)ad.samples_per_axis, xyza.as<double>(), nullptr, nullptr, nullptr,
+                                             (uint64_t*)ctx->d_counters, s);
+                if (rc) return rc;
+                st.rays_supersample = (uint64_t)n_sel * ad.samples_per_axis * ad.samples_per_axis;
+            }
+        }
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ev[3], s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(xyza_out, xyza.p, n * 32, cudaMemcpyDeviceToHost, s));
+    if (ray_class_out) CUDA_TRY(ctx, cudaMemcpyAsync(ray_class_out, cls.p, n, cudaMemcpyDeviceToHost, s));
+    if (stop_reason_out) CUDA_TRY(ctx, cudaMemcpyAsync(stop_reason_out, stop.p, n, cudaMemcpyDeviceToHost, s));
+    if (steps_out) CUDA_TRY(ctx, cudaMemcpyAsync(steps_out, steps.p, n * 4, cudaMemcpyDeviceToHost, s));
+    unsigned long long c[16];
+    CUDA_TRY(ctx, cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    st.attempts = c[CNT_ATTEMPTS];
+    st.accepted_steps = c[CNT_ACCEPTED];
+    st.raymarch_samples = c[CNT_SAMPLES];
+    st.ray_errors = c[CNT_ERRORS];
+    st.hit_stack_overflows = c[CNT_OVERFLOW];
+    for (int k = 0; k < 6; ++k) st.stop_histogram[k] = c[CNT_STOP0 + k];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); st.device_ms_base = ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]); st.device_ms_mask = ms;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]); st.device_ms_supersample = ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[3]); st.device_ms_total = ms;
+    if (stats) *stats = st;
+    return GRRT_OK;
+}
+
+static int trace_single(GrrtCtx* ctx, const GrrtScene* scene, const double* pos, const double* mom, int use_pixel,
+                        int64_t row, int64_t col, GrrtStep* steps_out, uint64_t cap, uint64_t* n_out, int32_t* stop_reason) {
+    if (!ctx || !scene || !n_out || !stop_reason) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GrrtDeviceScene* ds = nullptr;
+    int rc = grrt_scene_upload(ctx, scene, &ds);
+    if (rc) return rc;
+    struct Guard {
+        GrrtCtx* c;
+        GrrtDeviceScene* d;
+        ~Guard() { grrt_scene_free(c, d); }
+    } guard{ctx, ds};
+    if (!steps_out) cap = 0;
+    DevBuf dsteps, meta;
+    CUDA_TRY(ctx, dsteps.alloc(cap * sizeof(GrrtStep)));
+    CUDA_TRY(ctx, meta.alloc(32));
+    double4 p4 = make_double4(0, 0, 0, 0), m4 = make_double4(0, 0, 0, 0);
+    if (!use_pixel) {
+        p4 = make_double4(pos[0], pos[1], pos[2], pos[3]);
+        m4 = make_double4(mom[0], mom[1], mom[2], mom[3]);
+    }
+    unsigned long long* d_n = meta.as<unsigned long long>();
+    int* d_stop = reinterpret_cast<int*>(d_n + 1);
+    int* d_err = d_stop + 1;
+    cudaStream_t s = ctx->stream;
+#define LAUNCH_SINGLE(G)                                                                                          \
+    trace_single_kernel<G><<<1, 32, 0, s>>>(ds->s, p4, m4, use_pixel, (long long)row, (long long)col,            \
+                                            dsteps.as<GrrtStep>(), cap, d_n, d_stop, d_err)
+    switch (ds->s.geom) {
+        case GRRT_GEOM_EUCLIDEAN: LAUNCH_SINGLE(GRRT_GEOM_EUCLIDEAN); break;
+        case GRRT_GEOM_EUCLIDEAN_SPHERICAL: LAUNCH_SINGLE(GRRT_GEOM_EUCLIDEAN_SPHERICAL); break;
+        case GRRT_GEOM_SCHWARZSCHILD: LAUNCH_SINGLE(GRRT_GEOM_SCHWARZSCHILD); break;
+        case GRRT_GEOM_KERR: LAUNCH_SINGLE(GRRT_GEOM_KERR); break;
+        case GRRT_GEOM_KERR_BL: LAUNCH_SINGLE(GRRT_GEOM_KERR_BL); break;
+        default: return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "unknown geometry kind");
+    }
+#undef LAUNCH_SINGLE
+    CUDA_TRY(ctx, cudaGetLastError());
+    unsigned long long n = 0;
+    int sr[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(&n, d_n, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(sr, d_stop, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    uint64_t m = std::min<uint64_t>(n, cap);
+    if (m) CUDA_TRY(ctx, cudaMemcpy(steps_out, dsteps.p, m * sizeof(GrrtStep), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    *stop_reason = sr[0];
+    return sr[1];  // GRRT_RAYERR_* (>0) of the ray, 0 when it integrated
+}
+
+int grrt_trace_ray(GrrtCtx* ctx, const GrrtScene* scene, const double pos[4], const double mom[4], GrrtStep* steps_out,
+                   uint64_t cap, uint64_t* n_out, int32_t* stop_reason) {
+    if (!pos || !mom) return GRRT_ERR_INVALID_ARGUMENT;
+    return trace_single(ctx, scene, pos, mom, 0, 0, 0, steps_out, cap, n_out, stop_reason);
+}
+int grrt_trace_pixel_ray(GrrtCtx* ctx, const GrrtScene* scene, int64_t row, int64_t col, GrrtStep* steps_out,
+                         uint64_t cap, uint64_t* n_out, int32_t* stop_reason) {
+    return trace_single(ctx, scene, nullptr, nullptr, 1, row, col, steps_out, cap, n_out, stop_reason);
+}
+
+// test hook: the device's glibc-compatible pow on host arrays (tests/test_gpu_parity.py)
+int grrt_debug_pow(GrrtCtx* ctx, const double* x, const double* y, double* out, size_t n) {
+    if (!ctx || !x || !y || !out) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf dx, dy, dout;
+    CUDA_TRY(ctx, dx.alloc(n * 8));
+    CUDA_TRY(ctx, dy.alloc(n * 8));
+    CUDA_TRY(ctx, dout.alloc(n * 8));
+    CUDA_TRY(ctx, cudaMemcpy(dx.p, x, n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(dy.p, y, n * 8, cudaMemcpyHostToDevice));
+    if (n) debug_pow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dx.as<double>(), dy.as<double>(), dout.as<double>(), n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy(out, dout.p, n * 8, cudaMemcpyDeviceToHost));
+    return GRRT_OK;
+}
+
+int grrt_measure_fp64_peak(GrrtCtx* ctx, double* dfma_per_second, double* ms_out) {
+    if (!ctx || !dfma_per_second) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->num_sms * 8, threads = 256, iters = 20000;
+    DevBuf out;
+    CUDA_TRY(ctx, out.alloc((size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(ctx, cudaEventCreate(&e0));
+    CUDA_TRY(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, ctx->stream);
+        dfma_chain_kernel<<<blocks, threads, 0, ctx->stream>>>(out.as<double>(), iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CUDA_TRY(ctx, cudaGetLastError());
+    double n_fma = (double)blocks * threads * (double)iters * 64.0;
+    *dfma_per_second = n_fma / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return GRRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,597 @@
+// grrt_trace.cuh -- the persistent ray-tracing kernel (K1/K3 of SURVEY.md section 2).
+//
+// Scheduling: a fixed grid of persistent CTAs; every lane owns one ray at a time and pulls the
+// next work unit from a global atomic counter the moment its ray terminates (one atomicAdd per
+// warp, lanes ranked with ballot/popc).  All lanes of a warp therefore execute the same RKF45
+// attempt code on every trip of the main loop regardless of which ray or step they are on, so
+// the 100x spread in steps-per-ray (171 ... 15 500 ... 276 733) never idles a lane; only the
+// rare per-ray events (ray set-up, object shading, terminal colour) diverge.
+//
+// The reference stores the whole trajectory (112 B per step) and walks it a second time
+// (scene.rs:141-152); here each accepted step is tested against the objects as it is produced
+// and only the previous state is kept (in shared memory: it is read only when a hit occurs).
+//
+// VolumetricDisc ray-marches are executed warp-cooperatively: the lane that found the hit
+// broadcasts the march, the 32 lanes evaluate 32 consecutive samples in parallel (density,
+// Perlin fBm, redshift, LUT colour) and the order-dependent accumulation (transparency product,
+// emission sums) is then replayed in sample order so the result is the same sequence of
+// floating-point operations the reference performs (volumetric_disc.rs:209-328).
+#pragma once
+
+#include "grrt_device.cuh"
+#include "grrt_pow.cuh"
+
+namespace grrt {
+
+constexpr int kTraceThreads = 128;
+constexpr int kMaxHits = 32;
+constexpr int kMaxRetryStep = 100;  // runge_kutta.rs:60
+constexpr unsigned kFull = 0xffffffffu;
+
+enum { CNT_ATTEMPTS = 0, CNT_ACCEPTED = 1, CNT_SAMPLES = 2, CNT_ERRORS = 3, CNT_OVERFLOW = 4, CNT_RAYS = 5,
+       CNT_STOP0 = 8 /* 8..13 */ };
+
+struct TraceArgs {
+    const uint32_t* items;      // nullable: pixel ids (row-major within the rectangle)
+    unsigned long long first_item;
+    unsigned long long n_items;
+    unsigned long long n_units;  // work units handed out by the queue
+    uint32_t from_row, from_col, width, height;
+    uint32_t spa;                // 0: centre ray per item;  N: N*N stratified sub-samples per item
+    uint32_t tiled;              // items == NULL && spa == 0: units enumerate 8x4 pixel tiles
+    uint32_t tiles_x;
+    double* xyza;                // spa == 0: per item;  spa > 0: per unit
+    uint8_t* cls;
+    uint8_t* stop;
+    uint32_t* steps;
+    uint8_t* sub_valid;          // spa > 0: per unit
+    unsigned long long* queue;
+    unsigned long long* counters;
+};
+
+struct RayCtx {  // per-lane ray bookkeeping that is not touched inside an attempt
+    double freq_e, freq_pt, freq_pphi;
+    V3 prev_cart;
+    double opacity;
+    unsigned long long unit;
+    unsigned long long step;
+    int n_hits;
+    int retries;
+};
+
+template <int G>
+GD void camera_ray(const DScene& S, double row, double column, double pos[4], double mom[4]) {  // camera.rs:214-254
+    double shifted_column = column + 1.0;
+    double shifted_row = row + 1.0;
+    double i_prime = S.cam_hand * S.cam_scale * (shifted_column - (S.cam_cols + 1.0) / 2.0);
+    double j_prime = S.cam_scale * (shifted_row - (S.cam_rows + 1.0) / 2.0);
+    double w_squared = S.cam_sig * (1.0 + i_prime * i_prime + j_prime * j_prime);
+    double den = S.cam_sig * w_squared;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double w = (S.tet[3][i] + i_prime * S.tet[1][i]) + j_prime * S.tet[2][i];
+        double dir = -S.tet[3][i] + (2.0 * w) / den;
+        mom[i] = dir + (-S.tet[0][i]);
+        pos[i] = S.cam_pos[i];
+    }
+}
+
+// get_geodesic_solver + create_initial_state + get_ray_frequency_data
+template <int G>
+GD void init_ray(const DScene& S, const double pos[4], const double mom[4], double y[8], RayConst& C, RayCtx& R) {
+    C.e = C.l_z = C.q = 0.0;
+    if (G == GRRT_GEOM_KERR_BL) {  // kerr_bl.rs:505-577 (BL branch), 176-223
+        double r = pos[1];
+        double st, ct;
+        sincos(pos[2], &st, &ct);
+        BlMetric g = bl_metric(S.radius, S.a, r, st, ct);
+        // p_cov = g * p with nalgebra's accumulation (zero entries kept)
+        double pc0 = ((g.tt * mom[0] + 0.0 * mom[1]) + 0.0 * mom[2]) + g.tph * mom[3];
+        double pc2 = ((0.0 * mom[0] + 0.0 * mom[1]) + g.thth * mom[2]) + 0.0 * mom[3];
+        double pc3 = ((g.tph * mom[0] + 0.0 * mom[1]) + 0.0 * mom[2]) + g.phph * mom[3];
+        double e = -pc0, l_z = pc3, p_theta = pc2;
+        double sin2 = st * st;
+        double q = p_theta * p_theta + ct * ct * (l_z * l_z / fmax(sin2, 1e-28) - S.a * S.a * e * e);
+        C.e = e; C.l_z = l_z; C.q = q;
+        double a = S.a;
+        double sign_r = mom[1] >= 0.0 ? 1.0 : -1.0;
+        double sign_theta = mom[2] >= 0.0 ? 1.0 : -1.0;
+        double del = bl_delta(r, S.radius, a);
+        double p_r = (r * r + a * a) * e - a * l_z;
+        double lae = l_z - a * e;
+        double r_pot = p_r * p_r - del * (lae * lae + q);
+        double th_pot = q + a * a * e * e * ct * ct - l_z * l_z * ct * ct / (st * st);
+        y[0] = pos[0]; y[1] = r; y[2] = pos[2]; y[3] = pos[3];
+        y[4] = sign_r * sqrt(fmax(r_pot, 0.0));
+        y[5] = sign_theta * sqrt(fmax(th_pot, 0.0));
+        y[6] = 0.0; y[7] = 0.0;
+    } else if (G == GRRT_GEOM_KERR) {  // kerr.rs:243-260
+        double g10[10], m[4][4], pc[4];
+        ks_metric10(S.radius, S.a, pos[1], pos[2], pos[3], g10);
+        sym10_to_16(g10, m);
+        mat4_vec(m, mom, pc);
+        y[0] = pos[0]; y[1] = pos[1]; y[2] = pos[2]; y[3] = pos[3];
+        y[4] = pc[0]; y[5] = pc[1]; y[6] = pc[2]; y[7] = pc[3];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            y[i] = pos[i];
+            y[4 + i] = mom[i];
+        }
+    }
+    // redshift.rs:45-60
+    double e_t[4] = {1.0, 0.0, 0.0, 0.0};
+    double axial[4] = {0.0, 0.0, 0.0, 1.0};
+    if (GeomTraits<G>::chart == CH_CART) {
+        axial[1] = -pos[2]; axial[2] = pos[1]; axial[3] = 0.0;
+    }
+    R.freq_e = inner_product<G>(S, pos, S.cam_vel, mom);
+    R.freq_pt = inner_product<G>(S, pos, e_t, mom);
+    R.freq_pphi = inner_product<G>(S, pos, axial, mom);
+}
+
+// ---- warp-cooperative VolumetricDisc ray-march (volumetric_disc.rs:209-328) --------------------------
+// Every argument is warp-uniform.  Returns the march colour; *err receives a GRRT_RAYERR_* when
+// compute_temperature failed (the caller turns that into (0,0,0,0) as color_at_uv does, :596-600).
+template <int G>
+__device__ __noinline__ Cie vol_march_warp(const DScene& S, const DObject& o, const uint8_t* perm, V3 ro, V3 rd,
+                                           double e_obs, double p_t, double p_phi, int* err,
+                                           unsigned long long* samples) {
+    const int lane = threadIdx.x & 31;
+    const double sigma = o.absorption + o.scattering;
+    const double d_s = o.vol_step;
+    const V3 axis = obj_axis(o);
+    // precompute_exit_distance (:172-196)
+    double exit_distance = 0.0;
+    bool cached;
+    {
+        double max_distance = o.vol_step * (double)o.vol_max_steps;
+        V3 to = ro + rd * max_distance;
+        double t;
+        cached = vol_first_hit(o, ro, to, t);
+        if (cached) exit_distance = t * max_distance;
+    }
+    double transparency = 1.0, aws = 0.0, awt = 0.0, ax = 0.0, ay = 0.0, az = 0.0;
+    double D = 0.0;  // d_o at the first sample of the current block of 32
+    const unsigned long long max_steps = o.vol_max_steps;
+    *err = 0;
+    for (unsigned long long base = 0; base < max_steps; base += 32) {
+        double d_o = D;  // d_o is accumulated by repeated addition in the reference: replay it
+        for (int j = 0; j < 31; ++j)
+            if (j < lane) d_o += d_s;
+        const bool valid = base + (unsigned long long)lane < max_steps;
+        V3 p = ro + rd * d_o;
+        double d_o_next = d_o + d_s;
+        double density = valid ? vol_density(o, perm, p) : 0.0;
+        const bool has = density > 0.0;
+        double att = 1.0, light_att = 0.0, intensity = 0.0;
+        Cie light = cie(0.0, 0.0, 0.0, 0.0);
+        bool emit = false;
+        int terr = 0;
+        if (has) {
+            att = exp(-d_s * density * sigma);
+            double u_t, u_phi;
+            if (orbit_coefficients_cart<G>(S, p, u_t, u_phi)) {
+                double emitter_energy = u_t * p_t + u_phi * p_phi;
+                double redshift = e_obs / emitter_energy;
+                double r_dist = norm3(cross3(p, axis));
+                double temperature;
+                terr = compute_temperature(o.temp, r_dist, temperature);
+                if (!terr) {
+                    double u, v;
+                    vol_get_uv(o, p, u, v);
+                    light = texture_color(S, o.tex, u, v, temperature, redshift);
+                    light_att = exp(-density * d_s * sigma);
+                    double tr = temperature / o.bref_temperature;
+                    double tr2 = tr * tr;
+                    intensity = tr2 * tr2;
+                    emit = true;
+                }
+            }
+        }
+        bool exited = false;
+        if (valid) {
+            if (cached) {
+                exited = d_o_next >= exit_distance;
+            } else {  // does_exit (:154-170)
+                V3 to = v3(p.x + rd.x * d_s, p.y + rd.y * d_s, p.z + rd.z * d_s);
+                double t;
+                exited = vol_first_hit(o, p, to, t) && in01(t);
+            }
+        }
+        const unsigned m_valid = __ballot_sync(kFull, valid);
+        const unsigned m_exit = __ballot_sync(kFull, exited);
+        const unsigned m_err = __ballot_sync(kFull, terr != 0);
+        const unsigned m_has = __ballot_sync(kFull, has);
+        const unsigned m_emit = __ballot_sync(kFull, emit);
+        const int first_exit = m_exit ? (__ffs(m_exit) - 1) : 32;
+        const int first_err = m_err ? (__ffs(m_err) - 1) : 32;
+        const int last = min(first_exit, __popc(m_valid) - 1);  // last sample of this block that runs
+        if (first_err <= last) {
+            *err = __shfl_sync(kFull, terr, first_err);
+            *samples += (unsigned long long)(first_err + 1);
+            return cie(0.0, 0.0, 0.0, 0.0);
+        }
+        const unsigned upto = (last >= 31) ? kFull : ((1u << (last + 1)) - 1u);
+        // transparency *= sample_attenuation, in sample order
+        double my_t = transparency;
+        for (unsigned mm = m_has & upto; mm; mm &= mm - 1) {
+            int j = __ffs(mm) - 1;
+            transparency *= __shfl_sync(kFull, att, j);
+            if (j == lane) my_t = transparency;
+        }
+        double cx = 0.0, cy = 0.0, cz = 0.0, asw = 0.0, aw = 0.0;
+        if (emit) {
+            double emission_weight = my_t * light_att * o.scattering * density * d_s;
+            double f = emission_weight * intensity;
+            cx = light.x * f;
+            cy = light.y * f;
+            cz = light.z * f;
+            aw = density * d_s;
+            asw = rclamp(light.a, 0.0, 1.0) * aw;
+        }
+        for (unsigned mm = m_emit & upto; mm; mm &= mm - 1) {
+            int j = __ffs(mm) - 1;
+            aws += __shfl_sync(kFull, asw, j);
+            awt += __shfl_sync(kFull, aw, j);
+            ax += __shfl_sync(kFull, cx, j);
+            ay += __shfl_sync(kFull, cy, j);
+            az += __shfl_sync(kFull, cz, j);
+        }
+        *samples += (unsigned long long)(last + 1);
+        if (first_exit <= last) break;
+        D = __shfl_sync(kFull, d_o_next, 31);
+    }
+    double physical_opacity = 1.0 - transparency;
+    double texture_alpha = awt > 0.0 ? aws / awt : 1.0;
+    return cie(ax, ay, az, physical_opacity * texture_alpha);
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+enum { ST_IDLE = 0, ST_ACTIVE = 1, ST_DEAD = 2 };
+
+template <int G, bool HAS_VOL>
+__global__ void __launch_bounds__(kTraceThreads)
+trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs A) {
+    __shared__ double s_yprev[8][kTraceThreads];
+    __shared__ uint8_t s_perm[HAS_VOL ? GRRT_MAX_OBJECTS : 1][256];
+    __shared__ double s_pow_log[128][3];           // glibc-compatible pow tables (grrt_pow.cuh): divergent lookups
+    __shared__ unsigned long long s_pow_exp[256];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    for (int i = tid; i < 128 * 3; i += kTraceThreads) (&s_pow_log[0][0])[i] = (&kPowLogTab[0][0])[i];
+    for (int i = tid; i < 256; i += kTraceThreads) s_pow_exp[i] = kExpTab[i];
+    PowTables pow_tab;
+    pow_tab.log_tab = s_pow_log;
+    pow_tab.exp_tab = s_pow_exp;
+    if (HAS_VOL) {
+        for (int k = 0; k < S.n_objects; ++k)
+            if (S.obj[k].kind == GRRT_OBJ_VOLUMETRIC_DISC)
+                for (int i = tid; i < 256; i += kTraceThreads) s_perm[S.obj[k].perm_slot][i] = S.obj[k].perm[i];
+    }
+    __syncthreads();
+
+    int state = ST_IDLE;
+    double y[8];
+    double h = 0.0, h_cur = 0.0;
+    RayConst C = {0.0, 0.0, 0.0};
+    RayCtx R;
+    R.n_hits = 0; R.retries = 0; R.opacity = 0.0; R.unit = 0; R.step = 0;
+    R.freq_e = R.freq_pt = R.freq_pphi = 0.0;
+    R.prev_cart = v3(0.0, 0.0, 0.0);
+    Cie hits[kMaxHits];
+    unsigned long long c_attempts = 0, c_accepted = 0, c_samples = 0, c_errors = 0, c_overflow = 0, c_rays = 0;
+    unsigned long long ray_attempts = 0;
+    const unsigned ss = A.spa ? A.spa * A.spa : 1u;
+
+    for (;;) {
+        // ---------------- refill idle lanes from the global queue ----------------
+        const unsigned need = __ballot_sync(kFull, state == ST_IDLE);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(A.queue, (unsigned long long)__popc(need));
+            base = __shfl_sync(kFull, base, leader);
+            if (state == ST_IDLE) {
+                const unsigned long long unit = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
+                if (unit >= A.n_units) {
+                    state = ST_DEAD;
+                } else {
+                    // unit -> (item, stratum) -> pixel
+                    unsigned long long item = unit / ss;
+                    unsigned k = (unsigned)(unit % ss);
+                    unsigned long long pid;
+                    bool ok = true;
+                    if (A.tiled) {
+                        unsigned long long tile = unit >> 5;
+                        unsigned in_tile = (unsigned)(unit & 31);
+                        unsigned px = (unsigned)(tile % A.tiles_x) * 8u + (in_tile & 7u);
+                        unsigned py = (unsigned)(tile / A.tiles_x) * 4u + (in_tile >> 3);
+                        ok = px < A.width && py < A.height;
+                        pid = (unsigned long long)py * A.width + px;
+                        item = pid;
+                    } else {
+                        pid = A.items ? (unsigned long long)A.items[item] : A.first_item + item;
+                    }
+                    if (ok) {
+                        const long long row = (long long)(pid / A.width) + A.from_row;
+                        const long long col = (long long)(pid % A.width) + A.from_col;
+                        double frow = (double)row, fcol = (double)col;
+                        if (A.spa) {  // stratified_sample_offset + get_ray_for_offset (raytracer.rs:145-159, camera.rs:247-254)
+                            unsigned sr = k / A.spa, sc = k % A.spa;
+                            unsigned long long sample_index = (unsigned long long)sr * A.spa + sc;
+                            double dx = ((double)sc + hash_pixel_samples(row, col, 2ull * sample_index)) / (double)A.spa;
+                            double dy = ((double)sr + hash_pixel_samples(row, col, 2ull * sample_index + 1ull)) / (double)A.spa;
+                            frow = (double)row + (dy - 0.5);
+                            fcol = (double)col + (dx - 0.5);
+                        }
+                        double pos[4], mom[4];
+                        camera_ray<G>(S, frow, fcol, pos, mom);
+                        init_ray<G>(S, pos, mom, y, C, R);
+                        R.unit = A.tiled ? item : unit;
+                        R.step = 0;
+                        R.n_hits = 0;
+                        R.retries = 0;
+                        R.opacity = 0.0;
+                        R.prev_cart = position_cartesian<G>(S, y);
+                        h = S.step_size;
+                        h_cur = rclamp(h, kHMin, kHMax);
+                        ray_attempts = 0;
+                        state = ST_ACTIVE;
+                        ++c_rays;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(kFull, state != ST_DEAD) == 0) break;
+
+        const bool active = state == ST_ACTIVE;
+        int finish = -1;       // >= 0: GRRT_STOP_* with which this lane's ray ends on this trip
+        int ray_error = 0;
+        bool budget_empty = active && (S.max_steps <= 1);  // `for i in 1..max_steps` runs zero times
+        if (budget_empty) finish = GRRT_STOP_NONE;
+
+        // ---------------- one RKF45 attempt (runge_kutta.rs:138-182, flattened retry loop) ----------------
+        double y_new[8];
+        double err = 0.0;
+        bool accepted = false;
+        if (active && !budget_empty) {
+            rkf45_step<G>(S, C, y, h_cur, y_new, err);
+            ++ray_attempts;
+            double h_proposed;
+            if (err > 0.0) h_proposed = 0.9 * h_cur * pow_glibc(pow_tab, S.epsilon / err, 1.0 / 5.0);
+            else h_proposed = h_cur * kHGrowthCap;
+            h_proposed = rclamp(fmin(h_proposed, h_cur * kHGrowthCap), kHMin, kHMax);
+            if (err > S.epsilon) {
+                if (h_cur <= kHMin) {
+                    accepted = true;  // accept what we have at the minimum step
+                    h = h_cur;
+                } else {
+                    h_cur = rclamp(h_proposed / 2.0, kHMin, kHMax);
+                    if (++R.retries >= kMaxRetryStep) {
+                        finish = GRRT_STOP_ERROR;
+                        ray_error = GRRT_RAYERR_RKF45_RETRIES;
+                    }
+                }
+            } else {
+                accepted = true;
+                h = (err / S.epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
+            }
+        }
+
+        // ---------------- accepted step: objects on the chord prev -> cur ----------------
+        V3 cart = v3(0.0, 0.0, 0.0);
+        bool have_hit = false;
+        int vol_k = -1;
+        Hit best;
+        best.u = best.v = best.t = 0.0;
+        best.point = best.dir = v3(0.0, 0.0, 0.0);
+        Cie hit_color = cie(0.0, 0.0, 0.0, 0.0);
+        if (accepted) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s_yprev[i][tid] = y[i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = y_new[i];
+            ++R.step;
+            R.retries = 0;
+            h_cur = rclamp(h, kHMin, kHMax);
+            cart = position_cartesian<G>(S, y);
+            // Objects::intersects (objects.rs:65-120)
+            double shortest = 1.7976931348623157e308;
+            int best_k = -1;
+            double best_temperature = 0.0, best_redshift = 0.0;
+            for (int k = 0; k < S.n_objects; ++k) {
+                const DObject& o = S.obj[k];
+                Hit hcur;
+                bool hit;
+                if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, R.prev_cart, cart, hcur);
+                else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, R.prev_cart, cart, hcur);
+                else hit = vol_intersects(o, R.prev_cart, cart, hcur);
+                if (!hit) continue;
+                double distance = norm3(hcur.point - R.prev_cart);
+                if (!(distance < shortest)) continue;
+                shortest = distance;
+                // step_at_intersection (objects.rs:27-44): exact point, lerped momentum
+                double yp[8], p0[4], p1[4], xs[4], ps[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i][tid];
+                momentum_from_state<G>(S, C, yp, p0);
+                momentum_from_state<G>(S, C, y, p1);
+                double s = 1.0 - hcur.t;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ps[i] = s * p0[i] + hcur.t * p1[i];
+                cartesian_to_native<G>(S, hcur.point, xs);
+                double vel[4];
+                if (o.kind == GRRT_OBJ_SPHERE) {
+                    stationary_velocity<G>(S, xs, vel);
+                } else if (!circular_orbit_velocity<G>(S, xs, vel)) {
+                    finish = GRRT_STOP_ERROR;
+                    ray_error = GRRT_RAYERR_NO_CIRCULAR_ORBIT;
+                    break;
+                }
+                double emitter_energy = inner_product<G>(S, xs, vel, ps);
+                best_redshift = (GeomTraits<G>::sig0 * R.freq_e) / (GeomTraits<G>::sig0 * emitter_energy);
+                if (o.kind == GRRT_OBJ_SPHERE) {
+                    best_temperature = o.sphere_temperature;
+                } else {
+                    int terr = compute_temperature(o.temp, radial_coordinate_cart<G>(S, hcur.point), best_temperature);
+                    if (terr) {
+                        finish = GRRT_STOP_ERROR;
+                        ray_error = terr;
+                        break;
+                    }
+                }
+                best = hcur;
+                best_k = k;
+            }
+            if (finish != GRRT_STOP_ERROR && best_k >= 0) {
+                have_hit = true;
+                const DObject& o = S.obj[best_k];
+                if (o.kind == GRRT_OBJ_VOLUMETRIC_DISC) vol_k = best_k;
+                else hit_color = texture_color(S, o.tex, best.u, best.v, best_temperature, best_redshift);
+            }
+        }
+
+        // ---------------- warp-cooperative ray-marches for lanes with a VolumetricDisc hit ----------------
+        if (HAS_VOL) {
+            unsigned pending = __ballot_sync(kFull, vol_k >= 0);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const int k = __shfl_sync(kFull, vol_k, src);
+                V3 ro, rd;
+                ro.x = __shfl_sync(kFull, best.point.x, src);
+                ro.y = __shfl_sync(kFull, best.point.y, src);
+                ro.z = __shfl_sync(kFull, best.point.z, src);
+                V3 dir;
+                dir.x = __shfl_sync(kFull, best.dir.x, src);
+                dir.y = __shfl_sync(kFull, best.dir.y, src);
+                dir.z = __shfl_sync(kFull, best.dir.z, src);
+                rd = dir / norm3(dir);  // .normalize() (volumetric_disc.rs:589-594)
+                const double fe = __shfl_sync(kFull, R.freq_e, src);
+                const double fpt = __shfl_sync(kFull, R.freq_pt, src);
+                const double fpp = __shfl_sync(kFull, R.freq_pphi, src);
+                int merr = 0;
+                unsigned long long smp = 0;
+                const DObject& o = S.obj[k];
+                Cie c = vol_march_warp<G>(S, o, s_perm[o.perm_slot], ro, rd, fe, fpt, fpp, &merr, &smp);
+                if (lane == src) {
+                    hit_color = c;  // a failed march yields (0,0,0,0) (volumetric_disc.rs:596-600)
+                    c_samples += smp;
+                }
+            }
+        }
+
+        // ---------------- bookkeeping of the accepted step, stop tests, terminal colour ----------------
+        if (accepted && finish != GRRT_STOP_ERROR) {
+            if (have_hit) {
+                if (R.n_hits < kMaxHits) {
+                    hits[R.n_hits++] = hit_color;
+                } else {  // fold into the last slot: "older over newer" keeps the compositing order
+                    hits[kMaxHits - 1] = blend(hit_color, hits[kMaxHits - 1]);
+                    ++c_overflow;
+                }
+                double alpha = rclamp(hit_color.a, 0.0, 1.0);
+                R.opacity = alpha + R.opacity * (1.0 - alpha);  // scene.rs:149-150
+            }
+            R.prev_cart = cart;
+            int st = should_stop<G>(S, y, cart, R.step);
+            if (st != GRRT_STOP_NONE) finish = st;
+            else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
+        }
+
+        if (finish >= 0) {
+            Cie result = cie(0.0, 0.0, 0.0, 1.0);
+            int ray_class = GRRT_CLASS_ESCAPED;
+            if (finish != GRRT_STOP_ERROR) {
+                // scene.rs:157-214
+                Cie terminal = cie(0.0, 0.0, 0.0, 1.0);
+                bool has_terminal = false;
+                if (finish == GRRT_STOP_HORIZON || finish == GRRT_STOP_CLOSED_ORBIT) {
+                    has_terminal = true;
+                    ray_class = GRRT_CLASS_CAPTURED;
+                } else if (finish == GRRT_STOP_CELESTIAL) {
+                    // get_uv_coordinates (scene.rs:222-231) on the last stored step
+                    double theta, phi;
+                    if (GeomTraits<G>::chart == CH_CART) {
+                        double r;
+                        cartesian_to_spherical(y[1], y[2], y[3], r, theta, phi);
+                    } else {
+                        theta = rem_euclid(y[2], kPi);
+                        phi = rem_euclid(y[3] + kPi, 2.0 * kPi) - kPi;
+                    }
+                    double u = (kPi + phi) / (2.0 * kPi);
+                    double v = theta / kPi;
+                    // compute_redshift (redshift.rs:31-34): static emitter at the last step
+                    double vel[4], p[4];
+                    stationary_velocity<G>(S, y, vel);
+                    momentum_from_state<G>(S, C, y, p);
+                    double emitter_energy = inner_product<G>(S, y, vel, p);
+                    double redshift = (GeomTraits<G>::sig0 * R.freq_e) / (GeomTraits<G>::sig0 * emitter_energy);
+                    terminal = texture_color(S, S.celestial, 1.0 - u, v, S.celestial_temperature, redshift);
+                    has_terminal = true;
+                    ray_class = GRRT_CLASS_ESCAPED;
+                } else {
+                    ray_class = GRRT_CLASS_CAPTURED;  // NaN or no terminal event
+                }
+                if (has_terminal) result = blend(result, terminal);
+                for (int k = R.n_hits - 1; k >= 0; --k) result = blend(result, hits[k]);
+                if (R.opacity >= S.hit_opacity_threshold) ray_class = GRRT_CLASS_HIT;
+            } else {
+                ++c_errors;
+            }
+            // write out
+            const unsigned long long o = R.unit;
+            if (A.spa == 0) {
+                double* dst = A.xyza + 4 * o;
+                dst[0] = result.x; dst[1] = result.y; dst[2] = result.z; dst[3] = result.a;
+                if (A.cls) A.cls[o] = (uint8_t)ray_class;
+                if (A.stop) A.stop[o] = (uint8_t)finish;
+                if (A.steps) A.steps[o] = (uint32_t)R.step;
+            } else {
+                double* dst = A.xyza + 4 * o;
+                dst[0] = result.x; dst[1] = result.y; dst[2] = result.z; dst[3] = result.a;
+                A.sub_valid[o] = finish != GRRT_STOP_ERROR ? 1 : 0;
+            }
+            c_attempts += ray_attempts;
+            c_accepted += R.step;
+            if (A.counters) atomicAdd(A.counters + CNT_STOP0 + finish, 1ull);
+            state = ST_IDLE;
+        }
+    }
+
+    // ---------------- counters: warp-reduce, one atomic per warp ----------------
+    if (A.counters) {
+        unsigned long long v[6] = {c_attempts, c_accepted, c_samples, c_errors, c_overflow, c_rays};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            unsigned long long x = v[k];
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(kFull, x, off);
+            if (lane == 0 && x) atomicAdd(A.counters + k, x);
+        }
+    }
+}
+
+// mean over the valid sub-samples, summed in stratum order (raytracer.rs:341-379)
+__global__ void resolve_subsamples_kernel(const double* sub_xyza, const uint8_t* sub_valid, const uint32_t* items,
+                                          unsigned long long n_items, unsigned ss, double* xyza) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    double sx = 0.0, sy = 0.0, sz = 0.0, sa = 0.0;
+    unsigned valid = 0;
+    for (unsigned k = 0; k < ss; ++k) {
+        unsigned long long u = i * ss + k;
+        if (sub_valid[u]) {
+            const double* c = sub_xyza + 4 * u;
+            sx = sx + c[0]; sy = sy + c[1]; sz = sz + c[2]; sa = sa + c[3];
+            ++valid;
+        }
+    }
+    if (valid > 0) {
+        double inv = 1.0 / (double)valid;
+        double* dst = xyza + 4ull * items[i];
+        dst[0] = sx * inv; dst[1] = sy * inv; dst[2] = sz * inv; dst[3] = sa * inv;
+    }
+}
+
+}  // namespace grrt

@@ -269,9 +269,9 @@ int grrt_trace_pixel_ray(GrrtCtx* ctx, const GrrtScene* scene, int64_t row, int6
 int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* scene, GrrtDeviceScene** out);
 void grrt_scene_free(GrrtCtx* ctx, GrrtDeviceScene* dscene);
 
-/* Trace `n_items` work items.  Item i is pixel items[i] = row * cols + col of the full
- * camera frame (items == NULL: pixel ids first_item .. first_item+n_items-1 of the
- * rectangle [from_row,to_row) x [from_col,to_col), row-major).  samples_per_axis == 0:
+/* Trace `n_items` work items.  Item i is pixel id items[i] of the rectangle
+ * [from_row,to_row) x [from_col,to_col), numbered row-major from its top-left corner
+ * (items == NULL: the consecutive ids first_item .. first_item+n_items-1).  samples_per_axis == 0:
  * one centre ray per item.  samples_per_axis == N > 0: N*N stratified sub-sample rays
  * per item (raytracer.rs:138-159) averaged over the valid ones; items whose sub-samples
  * all failed keep xyza untouched.  Outputs are indexed by i. */
@@ -299,6 +299,9 @@ int grrt_tonemap_device(GrrtCtx* ctx, const double* d_xyza, size_t n_pixels, int
 /* DFMA-chain microbenchmark: the measured FP64 issue-rate roofline denominator.
  * Returns FP64 warp-level lane-instructions per second (one DFMA = 1). */
 int grrt_measure_fp64_peak(GrrtCtx* ctx, double* dfma_per_second, double* ms);
+
+/* Test hook: evaluates the device's glibc-compatible pow (csrc/grrt_pow.cuh) on host arrays. */
+int grrt_debug_pow(GrrtCtx* ctx, const double* x, const double* y, double* out, size_t n);
 
 /* ---- host-side scene assembly (mirror of src/cli + src/configuration.rs) --------- */
 
