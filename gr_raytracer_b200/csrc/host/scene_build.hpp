@@ -1,0 +1,39 @@
+// scene_build.hpp -- host-side scene assembly (see scene_build.cpp)
+#pragma once
+
+#include <array>
+#include <cstdint>
+#include <list>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/grrt.h"
+#include "toml.hpp"
+
+namespace grrt_host {
+
+struct HostBitmap {
+    std::vector<uint8_t> rgba;
+    uint32_t width = 0, height = 0;
+};
+struct HostTempLut {
+    std::vector<double> r, t;
+    double r_isco = 0.0;
+};
+
+// Owns every buffer the GrrtScene points into.
+struct HostSceneData {
+    GrrtScene scene;
+    std::vector<HostBitmap> bitmaps;
+    std::list<HostTempLut> temp_luts;
+    std::vector<double> bb_log_t, bb_xyz;
+};
+
+int build_scene_from_toml(const std::string& text, const char* resource_root, const GrrtCliOpts& opts, HostSceneData& out,
+                          std::string& err);
+int ray_at(const GrrtGeometry& g, const double position_cartesian[3], const double direction[3], double pos_out[4],
+           double mom_out[4], std::string& err);
+void step_to_cartesian(const GrrtGeometry& g, const double x[4], double out[4]);
+
+}  // namespace grrt_host

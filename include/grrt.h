@@ -345,6 +345,8 @@ int grrt_host_write_png_rgb8(const char* path, const uint8_t* rgb, uint32_t widt
 int grrt_host_write_hdr_xyz(const char* path, const double* xyza, uint32_t width, uint32_t height);
 int grrt_host_read_png_rgba8(const char* path, uint8_t** rgba_out, uint32_t* width, uint32_t* height);
 void grrt_host_free(void* p);
+/* sizeof() of the ABI structs in declaration order (0 = GrrtGeometry ... 10 = GrrtCliOpts), for binding checks */
+size_t grrt_abi_sizeof(int which);
 
 #ifdef __cplusplus
 }
