@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s and RKF45 steps/s of the geodesic path on N B200s, next to the CPU oracle.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1..C5] [--impl reference]
+
+One "step" is one full frame of the workload: 1-spp base pass, adaptive mask, 4x4 supersampling of
+the flagged pixels (reference src/rendering/raytracer.rs:257-318).  Default workload: BASELINE.json
+configs[1] (kerr-bl.toml, 1500x1500, KerrBL a=0.499, adaptive 4x4).  `value` is Mrays/s with the
+scene resident in HBM; `e2e` goes through the C-ABI call grrt_render() with host buffers (scene
+upload and result read-back inside the timed region).  `--impl reference` times the CPU oracle
+(oracle/, a C++ restatement of the reference: the Rust reference cannot be built in this image) on
+all host cores on a bounded sample of the same frame.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+# BASELINE.json configs with the command lines of SURVEY.md 8(d)
+WORKLOADS = {
+    "C1": dict(desc="scenes/schwarzschild.toml 500x500 camera -16,0,3.5 theta=-3.142 max-steps 20000",
+               toml="scenes/schwarzschild.toml", opts=dict(width=500, height=500, camera_position=[-16.0, 0.0, 3.5], theta=-3.142)),
+    "C2": dict(desc="scenes/kerr-bl.toml 1500x1500 KerrBL a=0.499 camera -10,0,-0.5 theta=-3.14159 adaptive 4x4",
+               toml="scenes/kerr-bl.toml", opts=dict(width=1500, height=1500, camera_position=[-10.0, 0.0, -0.5], theta=-3.14159)),
+    "C3": dict(desc="scenes/kerr.toml 1500x1500 Kerr-Schild a=0.499 camera -10,0,-0.5 theta=1.52 psi=-1.57 max-steps 1000000",
+               toml="scenes/kerr.toml", opts=dict(width=1500, height=1500, camera_position=[-10.0, 0.0, -0.5], theta=1.52, psi=-1.57, max_steps=1000000)),
+    "C4": dict(desc="scenes/kerr-volumetric-streaky.toml 2048x2048 camera -17,0,1.5 theta=1.659 psi=-1.57 max-steps 1000000",
+               toml="scenes/kerr-volumetric-streaky.toml",
+               opts=dict(width=2048, height=2048, camera_position=[-17.0, 0.0, 1.5], theta=1.659, psi=-1.57, max_steps=1000000)),
+    "C5": dict(desc="scenes/schwarzschild-volumetric-dense.toml 8192x8192 camera -16,0,3.5 theta=-3.142",
+               toml="scenes/schwarzschild-volumetric-dense.toml",
+               opts=dict(width=8192, height=8192, camera_position=[-16.0, 0.0, 3.5], theta=-3.142)),
+}
+# algorithmic FP64 operations: per RKF45 attempt, per accepted step, per ray-march sample
+FLOPS_ATTEMPT = {0: 498, 1: 726, 2: 726, 3: 10302, 4: 858}   # by GRRT_GEOM_*; Kerr = reference finite-difference mode
+FLOPS_ACCEPTED = {0: 30, 1: 60, 2: 60, 3: 230, 4: 90}
+FLOPS_SAMPLE = 1000
+
+
+def ensure_resources():
+    res = os.path.join(ROOT, "resources")
+    if not os.path.exists(os.path.join(res, "celestial.png")):
+        sys.path.insert(0, os.path.join(ROOT, "scenes"))
+        import make_textures
+        make_textures.main(res)
+
+
+def algorithmic_flops(geom_kind, attempts, accepted, samples):
+    return attempts * FLOPS_ATTEMPT[geom_kind] + accepted * FLOPS_ACCEPTED[geom_kind] + samples * FLOPS_SAMPLE
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report that instead of guessing
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def strips(height, n_strips, rows_per_strip):
+    """Evenly spread horizontal strips: a bounded, representative sample of the frame for the CPU arm."""
+    n_strips = max(1, min(n_strips, height // rows_per_strip))
+    starts = [int(round(i * (height - rows_per_strip) / max(1, n_strips - 1))) for i in range(n_strips)] if n_strips > 1 else [(height - rows_per_strip) // 2]
+    return [(s, min(height, s + rows_per_strip)) for s in starts]
+
+
+def cpu_sample(osc, oscene, width, height, budget_s, threads_hint=None):
+    """Times the oracle on strips of the frame sized for ~budget_s seconds.  Returns dict."""
+    lib = osc.lib()
+    cores = lib.orc_num_threads()
+    # calibrate on one thin strip in the middle band of the frame
+    t0 = time.perf_counter()
+    r = osc.render(oscene, height // 3, 0, height // 3 + 2, width)
+    dt = time.perf_counter() - t0
+    rows = max(4, int(budget_s / max(dt / 2.0, 1e-4)))
+    rows_per_strip = 4
+    n_strips = max(1, rows // rows_per_strip)
+    sel = strips(height, n_strips, rows_per_strip)
+    rays = steps = att = samples = 0
+    t0 = time.perf_counter()
+    for (a, b) in sel:
+        r = osc.render(oscene, a, 0, b, width)
+        st = r["stats"]
+        rays += st["rays_base"] + st["rays_supersample"]
+        steps += st["accepted_steps"]
+        att += st["attempts"]
+        samples += st["raymarch_samples"]
+    dt = time.perf_counter() - t0
+    return dict(seconds=dt, rays=rays, steps=steps, attempts=att, samples=samples, cores=cores,
+                sample=f"{len(sel)} strips x {rows_per_strip} rows x {width} cols of the {width}x{height} frame "
+                       f"(base + mask + supersampling inside each strip)")
+
+
+def run_reference(args, wl):
+    """--impl reference: the CPU oracle on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gr_raytracer_b200 import abi
+    from oracle import scene as osc
+    ensure_resources()
+    opts = abi.default_cli_opts(**wl["opts"])
+    oscene = osc.scene_from_toml(os.path.join(ROOT, wl["toml"]), opts, ROOT)
+    W, H = wl["opts"]["width"], wl["opts"]["height"]
+    total_budget = 150.0
+    per_step = max(2.0, total_budget / (args.steps + args.warmup))
+    res = None
+    t_all = 0.0
+    tot = dict(rays=0, steps=0, attempts=0, samples=0)
+    for i in range(args.warmup + args.steps):
+        res = cpu_sample(osc, oscene, W, H, per_step)
+        if i >= args.warmup:
+            t_all += res["seconds"]
+            for k in tot:
+                tot[k] += res[k]
+    mrays = tot["rays"] / t_all / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "rkf45_steps_per_s": tot["steps"] / t_all, "rkf45_attempts_per_s": tot["attempts"] / t_all,
+        "config": {"workload": args.workload + ": " + wl["desc"], "sampled": True},
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": res["cores"], "kind": "port", "sample": res["sample"],
+                         "note": "C++ oracle (restatement of the Rust reference, OpenMP over pixels); the reference needs cargo, absent here"},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def scene_h2d_bytes(sc):
+    """Bytes grrt_render copies to the device per call: textures (deduplicated) + LUTs + parameter block."""
+    from gr_raytracer_b200 import abi
+    seen, total = set(), 0
+    texs = [sc.celestial] + [sc.objects[k].texture for k in range(sc.n_objects)]
+    for t in texs:
+        if t.kind == abi.TEX_BITMAP:
+            key = C.addressof(t.rgba.contents)
+            if key not in seen:
+                seen.add(key)
+                total += t.width * t.height * 4
+    for k in range(sc.n_objects):
+        o = sc.objects[k]
+        if o.kind != abi.OBJ_SPHERE and o.temperature.kind == abi.TEMP_LUT:
+            total += o.temperature.n * 16
+        if o.kind == abi.OBJ_VOLUMETRIC_DISC:
+            total += 256
+    total += sc.bb_lut_n * 32
+    return total + C.sizeof(abi.GrrtScene)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="grrt", choices=["grrt", "reference"])
+    ap.add_argument("--width", type=int, default=None, help="override the workload's frame size (not a bench value)")
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kerr-analytic", action="store_true", help="closed-form Kerr-Schild gradient instead of the reference's finite difference")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    wl["opts"] = dict(wl["opts"])
+    if args.width:
+        wl["opts"]["width"] = args.width
+    if args.height:
+        wl["opts"]["height"] = args.height
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    from gr_raytracer_b200 import abi, api
+    from gr_raytracer_b200.renderer import DeviceEngine, FrameRenderer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libgrrt has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ensure_resources() if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+
+    opts = abi.default_cli_opts(**wl["opts"])
+    scene = api.HostScene(os.path.join(ROOT, wl["toml"]), opts, ROOT)
+    if args.kerr_analytic:
+        scene.c.kerr_rhs_mode = abi.KERR_RHS_ANALYTIC
+    sc = scene.c
+    W, H = int(sc.camera.cols), int(sc.camera.rows)
+    ctx = api.Context(local_rank)
+    engine = DeviceEngine(ctx, scene)
+    fr = FrameRenderer(engine, sc.adaptive, W, H, rank, world)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # FP64 roofline denominator, measured here (MEASURED_PEAKS.json carries no FP64 number)
+    dfma_rate, _ = ctx.measure_fp64_peak()
+
+    for _ in range(args.warmup):
+        fr.render()
+        flush.fill_(1)
+    sync_all()
+    engine.counters.zero_()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    counts = None
+    sync_all()
+    for i in range(args.steps):
+        ev[i][0].record()
+        counts = fr.render()
+        ev[i][1].record()
+        flush.fill_(i & 1)       # L2 flush between timed iterations (not timed)
+    sync_all()
+    clocks = sampler.finish()
+    launches = ctx.launch_count() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    cnt = engine.counters.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms = float(t.item())
+    cnt = [int(v) for v in cnt.tolist()]
+    attempts, accepted, samples, errors = cnt[0], cnt[1], cnt[2], cnt[3]
+    rays_per_step = counts["rays_base"] + counts["rays_supersample"]
+    secs = ms * 1e-3
+    mrays = rays_per_step * args.steps / secs / 1e6
+    flops = algorithmic_flops(sc.geometry.kind if not args.kerr_analytic else 3, attempts, accepted, samples)
+    if args.kerr_analytic and sc.geometry.kind == abi.GEOM_KERR:
+        flops = attempts * 1580 + accepted * 230 + samples * FLOPS_SAMPLE
+
+    # per-kernel time of the dominant kernel (trace_kernel): separate timed pass with events around each launch
+    kern_ms, kern_flops = None, None
+    if world == 1:
+        engine.counters.zero_()
+        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        torch.cuda.synchronize()
+        e0.record()
+        engine.trace(None, fr.n, fr.rect, 0, fr.xyza, fr.cls, fr.stop, fr.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        base_cnt = [int(v) for v in engine.counters.tolist()]
+        n_sel = 0
+        if sc.adaptive.enabled and not sc.adaptive.show_sampling_mask:
+            engine.select(fr.xyza, fr.cls, H, W, fr.selected, fr.count)
+            n_sel = int(fr.count.item())
+        ss_ms = 0.0
+        if n_sel:
+            e2.record()
+            engine.trace(fr.selected, n_sel, fr.rect, int(sc.adaptive.samples_per_axis), fr.xyza)
+            e3.record()
+            torch.cuda.synchronize()
+            ss_ms = e2.elapsed_time(e3)   # includes the (tiny) resolve kernel
+        tot_cnt = [int(v) for v in engine.counters.tolist()]
+        n_launch = 1 + (1 if n_sel else 0)
+        kern_ms = (e0.elapsed_time(e1) + ss_ms) / n_launch
+        kern_flops = algorithmic_flops(sc.geometry.kind, tot_cnt[0], tot_cnt[1], tot_cnt[2]) / n_launch
+        if args.kerr_analytic and sc.geometry.kind == abi.GEOM_KERR:
+            kern_flops = (tot_cnt[0] * 1580 + tot_cnt[1] * 230 + tot_cnt[2] * FLOPS_SAMPLE) / n_launch
+
+    # end to end through the C ABI with host buffers (grrt_render: upload scene, trace, read back)
+    e2e = None
+    if world == 1:
+        ctx.render(scene)  # warm
+        t0 = time.perf_counter()
+        reps = max(1, min(args.steps, 3))
+        for _ in range(reps):
+            out = ctx.render(scene)
+        dt = (time.perf_counter() - t0) / reps
+        st = out["stats"]
+        e2e_rays = st["rays_base"] + st["rays_supersample"]
+        d2h = W * H * (32 + 1 + 1 + 4) + 16 * 8
+        e2e = {"value": e2e_rays / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": scene_h2d_bytes(sc), "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3, "api": "grrt_render (C ABI, host buffers)"}
+    else:
+        # N > 1: the public multi-GPU call is FrameRenderer.render(); add the host round trip of scene and result
+        sync_all()
+        t0 = time.perf_counter()
+        eng2 = DeviceEngine(ctx, scene)
+        fr2 = FrameRenderer(eng2, sc.adaptive, W, H, rank, world)
+        c2 = fr2.render()
+        host = fr2.xyza.cpu() if rank == 0 else None
+        sync_all()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": (c2["rays_base"] + c2["rays_supersample"]) / float(dt.item()) / 1e6, "unit": "Mrays/s",
+               "h2d_bytes_per_step": scene_h2d_bytes(sc) * world, "d2h_bytes_per_step": W * H * 32,
+               "ms_per_step": float(dt.item()) * 1e3, "api": "FrameRenderer.render + host copy (includes buffer allocation)"}
+        eng2.close()
+        del host
+
+    line = None
+    if rank == 0:
+        peak_tflops = 2.0 * dfma_rate / 1e12
+        roofline = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tflops,
+                    "peak_source": "DFMA-chain microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); FMA = 2 flops",
+                    "traffic": None}
+        if kern_ms:
+            ach = kern_flops / (kern_ms * 1e-3) / 1e12
+            roofline.update({"achieved": ach, "frac": ach / peak_tflops, "kernel": "trace_kernel", "kernel_ms_per_launch": kern_ms,
+                             "algorithmic_flops_per_launch": kern_flops,
+                             "note": "algorithmic FP64 ops of SURVEY.md 8(d) (divisions, sqrt and libm calls count 1 each); the kernel is "
+                                     "compiled without FMA contraction for bit-parity, so its issue-slot ceiling is half the FMA peak"})
+        else:
+            ach = flops / secs / 1e12
+            roofline.update({"achieved": ach, "frac": ach / (peak_tflops * world), "kernel": "whole step, all ranks"})
+        line = {
+            "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H, "l2": "256 MiB flush write between timed steps",
+                       "partition": "whole frame" if world == 1 else f"8x4 tiles round-robin over {world} ranks",
+                       "textures": "synthetic 2048x2048 atlases (scenes/make_textures.py)"},
+            "rays_per_step": rays_per_step, "pixels_supersampled": counts["pixels_supersampled"],
+            "rkf45_steps_per_s": accepted / secs, "rkf45_attempts_per_s": attempts / secs, "raymarch_samples_per_s": samples / secs,
+            "ray_errors": errors, "algorithmic_tflops": flops / secs / 1e12,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
+        }
+    # CPU baseline on rank 0 at N=1 only (bounded sample, all host cores)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import scene as osc
+        oscene = osc.scene_from_toml(os.path.join(ROOT, wl["toml"]), opts, ROOT)
+        res = cpu_sample(osc, oscene, W, H, 20.0)
+        line["cpu_baseline"] = {"value": res["rays"] / res["seconds"] / 1e6, "unit": "Mrays/s", "cores": res["cores"], "kind": "port",
+                                "sample": res["sample"], "rkf45_steps_per_s": res["steps"] / res["seconds"], "seconds": res["seconds"]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    engine.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+import ctypes as C  # noqa: E402
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,8 @@ def lib():
     L.grrt_version.restype = C.c_char_p
     L.grrt_init.argtypes = [C.c_int, C.POINTER(vp)]
     L.grrt_destroy.argtypes = [vp]
+    L.grrt_kernel_launch_count.argtypes = [vp]
+    L.grrt_kernel_launch_count.restype = C.c_ulonglong
     L.grrt_last_error.argtypes = [vp]
     L.grrt_last_error.restype = C.c_char_p
     L.grrt_render.argtypes = [vp, scene_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp, u8p, u8p, u32p,
@@ -209,6 +211,9 @@ class Context:
         m_ = min(n.value, cap)
         dt = np.dtype([("x", "f8", 4), ("p", "f8", 4), ("t", "f8"), ("step", "u8")])
         return np.frombuffer(buf, dtype=dt, count=m_).copy(), stop.value, err
+
+    def launch_count(self):
+        return int(lib().grrt_kernel_launch_count(self._h))
 
     def debug_pow(self, x, y):
         x = np.ascontiguousarray(x, dtype=np.float64)

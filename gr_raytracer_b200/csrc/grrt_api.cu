@@ -26,6 +26,7 @@ struct GrrtCtx {
     unsigned long long* d_counters = nullptr;  // 16 x u64
     void* d_cub_temp = nullptr;
     size_t cub_temp_bytes = 0;
+    unsigned long long launches = 0;  // kernels of this library launched so far (bench.py's gpu_launches)
 };
 
 struct GrrtDeviceScene {
@@ -308,6 +309,7 @@ int launch_trace_t(GrrtCtx* ctx, const DScene& s, const TraceArgs& a, cudaStream
     if (want < grid) grid = want;
     if (grid == 0) return GRRT_OK;
     trace_kernel<G, V><<<(unsigned)grid, kTraceThreads, 0, st>>>(s, a);
+    ++ctx->launches;
     CUDA_TRY(ctx, cudaGetLastError());
     return GRRT_OK;
 }
@@ -390,6 +392,8 @@ void grrt_destroy(GrrtCtx* ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+
+unsigned long long grrt_kernel_launch_count(const GrrtCtx* ctx) { return ctx ? ctx->launches : 0; }
 
 const char* grrt_last_error(const GrrtCtx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
 
@@ -561,6 +565,7 @@ int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint3
         if (rc) return rc;
         resolve_subsamples_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(sub.as<double>(), valid.as<uint8_t>(),
                                                                                 d_items + off, m, ss, d_xyza);
+        ++ctx->launches;
         CUDA_TRY(ctx, cudaGetLastError());
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(st));  // scratch is freed on return
@@ -587,6 +592,7 @@ int grrt_select_mask_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const doubl
         CUDA_TRY(ctx, keys_in.alloc(n * 8));
         CUDA_TRY(ctx, keys_out.alloc(n * 8));
         luminance_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyza, n, keys_in.as<unsigned long long>());
+        ++ctx->launches;
         size_t tmp = 0;
         CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys_in.as<unsigned long long>(),
                                                      keys_out.as<unsigned long long>(), (long long)n, 0, 64, st));
@@ -599,6 +605,7 @@ int grrt_select_mask_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const doubl
     }
     mask_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyza, d_class, rows, cols, ds->adaptive, key_at,
                                                                     minlum.as<double>(), flags.as<uint8_t>());
+    ++ctx->launches;
     CUDA_TRY(ctx, cudaGetLastError());
     {
         cub::CountingInputIterator<uint32_t> ids(0);
@@ -626,8 +633,10 @@ int grrt_tonemap_device(GrrtCtx* ctx, const double* d_xyza, size_t n, int method
     if (method == GRRT_TONEMAP_GLOBAL_LINEAR) {
         CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, sizeof(double), st));
         linear_max_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyza, n, exposure, d_max);
+        ++ctx->launches;
     }
     tonemap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyza, n, method, exposure, d_max, d_rgb);
+    ++ctx->launches;
     CUDA_TRY(ctx, cudaGetLastError());
     return GRRT_OK;
 }
@@ -703,6 +712,7 @@ int grrt_render(GrrtCtx* ctx, const GrrtScene* scene, uint32_t from_row, uint32_
         if (n_sel) {
             if (ad.show_sampling_mask) {
                 fill_mask_color_kernel<<<(n_sel + 255) / 256, 256, 0, s>>>(sel.as<uint32_t>(), n_sel, ad, xyza.as<double>());
+                ++ctx->launches;
                 CUDA_TRY(ctx, cudaGetLastError());
             } else {
                 if (ad.samples_per_axis == 0 || ad.samples_per_axis > 4096)

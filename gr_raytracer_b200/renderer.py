@@ -1,0 +1,156 @@
+"""Frame driver on device-resident buffers: the two-pass adaptive render of
+`Raytracer::render_section_to_cie_buffer_supersampled` (reference src/rendering/raytracer.rs:257-318)
+for one GPU or for the ranks of a `torch.distributed` job.
+
+Multi-GPU (BASELINE.json north_star): pixels are independent, so the image is cut into 8x4-pixel
+tiles dealt round-robin to the ranks (fine-grained interleaving balances the spatially clustered
+shadow / disc work without a pilot pass).  The only coupling is the adaptive mask: it reads the 8
+neighbours of every pixel and a frame-global 99th-percentile luminance (raytracer.rs:118-129,
+386-458), so the 1-spp base buffer (33 B per pixel) is exchanged once with an all-gather; every rank
+then derives the same mask, supersamples its share of the flagged pixels and the per-pixel means are
+all-gathered.  No reduction is involved; the N-GPU image is bit-identical to the 1-GPU image.
+
+torch is plumbing here (device buffers, the current stream, the collective); the ray tracing, mask
+selection and tone mapping are the CUDA kernels of libgrrt.so reached through the C ABI.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+
+TILE_W, TILE_H = 8, 4
+
+
+def tile_interleaved_items(width, height, rank, world):
+    """Pixel ids (row-major within the frame) of the 8x4 tiles owned by `rank`, tile-major so that 32
+    consecutive work units are one compact patch."""
+    tiles_x = (width + TILE_W - 1) // TILE_W
+    tiles_y = (height + TILE_H - 1) // TILE_H
+    tiles = np.arange(rank, tiles_x * tiles_y, world, dtype=np.int64)
+    ty, tx = tiles // tiles_x, tiles % tiles_x
+    dy, dx = np.divmod(np.arange(TILE_W * TILE_H, dtype=np.int64), TILE_W)
+    py = (ty[:, None] * TILE_H + dy[None, :]).ravel()
+    px = (tx[:, None] * TILE_W + dx[None, :]).ravel()
+    ok = (py < height) & (px < width)
+    return (py[ok] * width + px[ok]).astype(np.uint32)
+
+
+class DeviceEngine:
+    """libgrrt.so on one CUDA device, operating on torch tensors."""
+
+    def __init__(self, ctx, scene):
+        self.ctx = ctx
+        self.scene = scene
+        self.dscene = ctx.upload(scene)
+        self.device = torch.device("cuda", ctx.device)
+        self.counters = torch.zeros(16, dtype=torch.int64, device=self.device)
+
+    def close(self):
+        if self.dscene is not None:
+            self.ctx.free_scene(self.dscene)
+            self.dscene = None
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def trace(self, items, n_items, rect, spa, xyza, cls=None, stop=None, steps=None):
+        self.ctx.trace_items_device(self.dscene, self._p(items), 0, n_items, rect, spa, self._p(xyza), self._p(cls),
+                                    self._p(stop), self._p(steps), self._p(self.counters), self._stream())
+
+    def select(self, xyza, cls, rows, cols, selected, count):
+        return self.ctx.select_mask_device(self.dscene, self._p(xyza), self._p(cls), rows, cols, self._p(selected),
+                                           self._p(count), self._stream())
+
+    def new(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+
+class FrameRenderer:
+    """One frame = base pass + mask + supersampling, sharded over `world` ranks."""
+
+    def __init__(self, engine, adaptive, width, height, rank=0, world=1, group=None):
+        self.e, self.ad = engine, adaptive
+        self.W, self.H = int(width), int(height)
+        self.rank, self.world, self.group = rank, world, group
+        n = self.W * self.H
+        self.n = n
+        self.rect = (0, 0, self.H, self.W)
+        self.xyza = engine.new((n, 4), torch.float64)
+        self.cls = engine.new((n,), torch.uint8)
+        self.stop = engine.new((n,), torch.uint8)
+        self.steps = engine.new((n,), torch.int32)
+        self.selected = engine.new((n,), torch.int32)
+        self.count = engine.new((1,), torch.int32)
+        if world > 1:
+            ids = tile_interleaved_items(self.W, self.H, rank, world)
+            self.my_items = torch.from_numpy(ids.astype(np.int32)).to(self.xyza.device)
+            self.n_mine = int(ids.size)
+            self.max_items = max(int(tile_interleaved_items(self.W, self.H, r, world).size) for r in range(world))
+            self.all_items = [torch.from_numpy(tile_interleaved_items(self.W, self.H, r, world).astype(np.int64)).to(self.xyza.device)
+                              for r in range(world)]
+            m = self.max_items
+            self.loc_xyza = engine.new((m, 4), torch.float64)
+            self.loc_cls = engine.new((m,), torch.uint8)
+            self.loc_stop = engine.new((m,), torch.uint8)
+            self.loc_steps = engine.new((m,), torch.int32)
+            self.gat_xyza = engine.new((world, m, 4), torch.float64)
+            self.gat_meta = engine.new((world, m, 2), torch.uint8)
+        self.last = {}
+
+    def _all_gather(self, out, inp):
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def render(self):
+        """Renders the frame into self.xyza / cls / stop / steps (device).  Returns ray counts."""
+        e, ad = self.e, self.ad
+        if self.world == 1:
+            e.trace(None, self.n, self.rect, 0, self.xyza, self.cls, self.stop, self.steps)
+        else:
+            e.trace(self.my_items, self.n_mine, self.rect, 0, self.loc_xyza, self.loc_cls, self.loc_stop, self.loc_steps)
+            meta = torch.stack((self.loc_cls, self.loc_stop), dim=1)
+            self._all_gather(self.gat_xyza.view(-1, 4), self.loc_xyza)
+            self._all_gather(self.gat_meta.view(-1, 2), meta)
+            for r in range(self.world):
+                idx = self.all_items[r]
+                k = idx.numel()
+                self.xyza.index_copy_(0, idx, self.gat_xyza[r, :k])
+                self.cls.index_copy_(0, idx, self.gat_meta[r, :k, 0])
+                self.stop.index_copy_(0, idx, self.gat_meta[r, :k, 1])
+        n_sel = 0
+        min_lum = 0.0
+        if ad.enabled or ad.show_sampling_mask:
+            min_lum = e.select(self.xyza, self.cls, self.H, self.W, self.selected, self.count)
+            n_sel = int(self.count.item())
+            if n_sel and ad.show_sampling_mask:
+                col = torch.tensor(list(ad.mask_xyza), dtype=torch.float64, device=self.xyza.device)
+                self.xyza[self.selected[:n_sel].long()] = col
+            elif n_sel:
+                spa = int(ad.samples_per_axis)
+                if self.world == 1:
+                    e.trace(self.selected, n_sel, self.rect, spa, self.xyza)
+                else:
+                    # flagged pixels dealt round-robin; every rank writes its means into a frame-sized scratch
+                    mine = self.selected[:n_sel][self.rank::self.world].contiguous()
+                    k = int(mine.numel())
+                    per = (n_sel + self.world - 1) // self.world
+                    loc = self.e.new((per, 4), torch.float64)
+                    scratch = self.xyza.clone()
+                    if k:
+                        e.trace(mine, k, self.rect, spa, scratch)
+                        loc[:k] = scratch[mine.long()]
+                    gat = self.e.new((self.world, per, 4), torch.float64)
+                    self._all_gather(gat.view(-1, 4), loc)
+                    for r in range(self.world):
+                        ids = self.selected[:n_sel][r::self.world].long()
+                        self.xyza.index_copy_(0, ids, gat[r, :ids.numel()])
+        ss = int(ad.samples_per_axis) ** 2 if (n_sel and not ad.show_sampling_mask) else 0
+        self.last = dict(rays_base=self.n, pixels_supersampled=n_sel, rays_supersample=n_sel * ss,
+                         minimum_luminance=min_lum)
+        return self.last

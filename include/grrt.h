@@ -238,6 +238,8 @@ int grrt_init(int device_id, GrrtCtx** out);
 void grrt_destroy(GrrtCtx* ctx);
 const char* grrt_last_error(const GrrtCtx* ctx);
 const char* grrt_version(void);
+/* Number of this library's own kernels launched through `ctx` so far (CUB/memset launches not counted). */
+unsigned long long grrt_kernel_launch_count(const GrrtCtx* ctx);
 
 /* Drop-in for Raytracer::render_section_to_cie_buffer (raytracer.rs:177-193): base
  * pass, adaptive mask, supersampling (or mask visualisation).  Outputs are caller-owned
