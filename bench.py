@@ -316,11 +316,17 @@ def main():
     # end to end through the C ABI with host buffers (grrt_render: upload scene, trace, read back)
     e2e = None
     if world == 1:
-        ctx.render(scene)  # warm
+        npx = W * H   # results land in pinned host memory
+        pinned = {"xyza": torch.empty((npx, 4), dtype=torch.float64).pin_memory().numpy(),
+                  "ray_class": torch.empty(npx, dtype=torch.uint8).pin_memory().numpy(),
+                  "stop": torch.empty(npx, dtype=torch.uint8).pin_memory().numpy(),
+                  "steps": torch.empty(npx, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+        for _ in range(2):
+            ctx.render(scene, out=pinned)  # warm
         t0 = time.perf_counter()
-        reps = max(1, min(args.steps, 3))
+        reps = max(1, min(args.steps, 5))
         for _ in range(reps):
-            out = ctx.render(scene)
+            out = ctx.render(scene, out=pinned)
         dt = (time.perf_counter() - t0) / reps
         st = out["stats"]
         e2e_rays = st["rays_base"] + st["rays_supersample"]

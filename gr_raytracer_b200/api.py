@@ -168,17 +168,23 @@ class Context:
             pass
 
     # -- Raytracer::render_section_to_cie_buffer -------------------------------------------------
-    def render(self, scene, from_row=None, from_col=None, to_row=None, to_col=None):
+    def render(self, scene, from_row=None, from_col=None, to_row=None, to_col=None, out=None):
+        """`out` (optional): dict of preallocated C-contiguous host arrays xyza[n,4] f64, ray_class[n] u8, stop[n] u8,
+        steps[n] u32 -- e.g. views of pinned torch tensors -- to avoid per-call allocation and pageable copies."""
         sc = _scene_struct(scene)
         fr = 0 if from_row is None else from_row
         fc = 0 if from_col is None else from_col
         tr = sc.camera.rows if to_row is None else to_row
         tc = sc.camera.cols if to_col is None else to_col
         n = (tr - fr) * (tc - fc)
-        xyza = np.zeros((n, 4))
-        cls = np.zeros(n, dtype=np.uint8)
-        stop = np.zeros(n, dtype=np.uint8)
-        steps = np.zeros(n, dtype=np.uint32)
+        if out is not None:
+            xyza, cls, stop, steps = out["xyza"], out["ray_class"], out["stop"], out["steps"]
+            assert xyza.size == 4 * n and cls.size == n and stop.size == n and steps.size == n
+        else:
+            xyza = np.zeros((n, 4))
+            cls = np.zeros(n, dtype=np.uint8)
+            stop = np.zeros(n, dtype=np.uint8)
+            steps = np.zeros(n, dtype=np.uint32)
         stats = abi.GrrtStats()
         self._check(lib().grrt_render(self._h, _scene_ptr(scene), fr, fc, tr, tc,
                                       xyza.ctypes.data_as(abi.c_double_p), cls.ctypes.data_as(abi.c_uint8_p),

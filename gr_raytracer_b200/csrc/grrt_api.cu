@@ -62,7 +62,7 @@ int upload(GrrtCtx* ctx, GrrtDeviceScene* ds, const T* host, size_t count, const
     *out = nullptr;
     if (!host || count == 0) return GRRT_OK;
     void* p = nullptr;
-    CUDA_TRY(ctx, cudaMalloc(&p, count * sizeof(T)));
+    CUDA_TRY(ctx, cudaMallocAsync(&p, count * sizeof(T), ctx->stream));
     ds->allocs.push_back(p);
     CUDA_TRY(ctx, cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     *out = static_cast<const T*>(p);
@@ -338,10 +338,17 @@ int ensure_cub_temp(GrrtCtx* ctx, size_t bytes) {
     return GRRT_OK;
 }
 
-struct DevBuf {  // RAII device allocation
+// RAII device allocation from the stream-ordered pool: after warm-up neither the allocation nor the release
+// touches the driver's page tables or synchronises the device (plain cudaMalloc/cudaFree cost up to hundreds
+// of milliseconds per frame here and serialise against running kernels).
+struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    cudaStream_t st = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        st = stream;
+        return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+    }
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
@@ -369,6 +376,13 @@ int grrt_init(int device_id, GrrtCtx** out) {
     }
     ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GRRT_ERR_CUDA; }
+    {  // keep freed blocks cached in the device's default memory pool instead of returning them to the OS
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     double lut[256];
     for (int i = 0; i < 256; ++i) lut[i] = inv_compand_srgb_host((double)i / 255.0);
     if (cudaMalloc(&ctx->d_srgb_lut, sizeof lut) != cudaSuccess ||
@@ -503,7 +517,8 @@ int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) 
 void grrt_scene_free(GrrtCtx* ctx, GrrtDeviceScene* ds) {
     if (!ds) return;
     if (ctx) cudaSetDevice(ctx->device);
-    for (void* p : ds->allocs) cudaFree(p);
+    cudaDeviceSynchronize();  // the scene may be in use on a caller's stream
+    for (void* p : ds->allocs) cudaFreeAsync(p, ctx ? ctx->stream : nullptr);
     delete ds;
 }
 
@@ -550,8 +565,8 @@ int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint3
     const uint64_t chunk_items = std::max<uint64_t>(1, (uint64_t)(1ull << 28) / ss);  // <= 8 GiB of scratch
     DevBuf sub, valid;
     const uint64_t cap = std::min<uint64_t>(chunk_items, n_items);
-    CUDA_TRY(ctx, sub.alloc(cap * ss * 4 * sizeof(double)));
-    CUDA_TRY(ctx, valid.alloc(cap * ss));
+    CUDA_TRY(ctx, sub.alloc(cap * ss * 4 * sizeof(double), st));
+    CUDA_TRY(ctx, valid.alloc(cap * ss, st));
     for (uint64_t off = 0; off < n_items; off += cap) {
         uint64_t m = std::min<uint64_t>(cap, n_items - off);
         a.items = d_items + off;
@@ -585,12 +600,12 @@ int grrt_select_mask_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const doubl
         return GRRT_OK;
     }
     DevBuf keys_in, keys_out, flags, minlum;
-    CUDA_TRY(ctx, flags.alloc(n));
-    CUDA_TRY(ctx, minlum.alloc(sizeof(double)));
+    CUDA_TRY(ctx, flags.alloc(n, st));
+    CUDA_TRY(ctx, minlum.alloc(sizeof(double), st));
     const unsigned long long* key_at = nullptr;
     if (!ds->adaptive.has_minimum_luminance) {  // 99th percentile by a full radix sort of total_cmp keys
-        CUDA_TRY(ctx, keys_in.alloc(n * 8));
-        CUDA_TRY(ctx, keys_out.alloc(n * 8));
+        CUDA_TRY(ctx, keys_in.alloc(n * 8, st));
+        CUDA_TRY(ctx, keys_out.alloc(n * 8, st));
         luminance_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyza, n, keys_in.as<unsigned long long>());
         ++ctx->launches;
         size_t tmp = 0;
@@ -645,8 +660,8 @@ int grrt_tonemap(GrrtCtx* ctx, const double* xyza, size_t n, int method, double 
     if (!ctx || !xyza || !rgb_out) return GRRT_ERR_INVALID_ARGUMENT;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     DevBuf in, out;
-    CUDA_TRY(ctx, in.alloc(n * 32));
-    CUDA_TRY(ctx, out.alloc(n * 3));
+    CUDA_TRY(ctx, in.alloc(n * 32, ctx->stream));
+    CUDA_TRY(ctx, out.alloc(n * 3, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(in.p, xyza, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     int rc = grrt_tonemap_device(ctx, in.as<double>(), n, method, exposure, out.as<uint8_t>(), ctx->stream);
     if (rc) return rc;
@@ -679,10 +694,10 @@ int grrt_render(GrrtCtx* ctx, const GrrtScene* scene, uint32_t from_row, uint32_
     }
     cudaStream_t s = ctx->stream;
     DevBuf xyza, cls, stop, steps, sel, cnt;
-    CUDA_TRY(ctx, xyza.alloc(n * 32));
-    CUDA_TRY(ctx, cls.alloc(n));
-    CUDA_TRY(ctx, stop.alloc(n));
-    CUDA_TRY(ctx, steps.alloc(n * 4));
+    CUDA_TRY(ctx, xyza.alloc(n * 32, s));
+    CUDA_TRY(ctx, cls.alloc(n, s));
+    CUDA_TRY(ctx, stop.alloc(n, s));
+    CUDA_TRY(ctx, steps.alloc(n * 4, s));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), s));
     cudaEvent_t ev[4];
     for (auto& e : ev) CUDA_TRY(ctx, cudaEventCreate(&e));
@@ -701,12 +716,13 @@ int grrt_render(GrrtCtx* ctx, const GrrtScene* scene, uint32_t from_row, uint32_
     uint32_t n_sel = 0;
     CUDA_TRY(ctx, cudaEventRecord(ev[2], s));
     if (ad.enabled || ad.show_sampling_mask) {  // raytracer.rs:184
-        CUDA_TRY(ctx, sel.alloc(n * 4));
-        CUDA_TRY(ctx, cnt.alloc(4));
+        CUDA_TRY(ctx, sel.alloc(n * 4, s));
+        CUDA_TRY(ctx, cnt.alloc(4, s));
         rc = grrt_select_mask_device(ctx, ds, xyza.as<double>(), cls.as<uint8_t>(), H, W, sel.as<uint32_t>(),
                                      cnt.as<uint32_t>(), &st.minimum_luminance, s);
         if (rc) return rc;
-        CUDA_TRY(ctx, cudaMemcpy(&n_sel, cnt.p, 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpyAsync(&n_sel, cnt.p, 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));
         CUDA_TRY(ctx, cudaEventRecord(ev[2], s));
         st.pixels_supersampled = n_sel;
         if (n_sel) {
@@ -762,8 +778,8 @@ static int trace_single(GrrtCtx* ctx, const GrrtScene* scene, const double* pos,
     } guard{ctx, ds};
     if (!steps_out) cap = 0;
     DevBuf dsteps, meta;
-    CUDA_TRY(ctx, dsteps.alloc(cap * sizeof(GrrtStep)));
-    CUDA_TRY(ctx, meta.alloc(32));
+    CUDA_TRY(ctx, dsteps.alloc(cap * sizeof(GrrtStep), ctx->stream));
+    CUDA_TRY(ctx, meta.alloc(32, ctx->stream));
     double4 p4 = make_double4(0, 0, 0, 0), m4 = make_double4(0, 0, 0, 0);
     if (!use_pixel) {
         p4 = make_double4(pos[0], pos[1], pos[2], pos[3]);
@@ -792,7 +808,10 @@ static int trace_single(GrrtCtx* ctx, const GrrtScene* scene, const double* pos,
     CUDA_TRY(ctx, cudaMemcpyAsync(sr, d_stop, 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     uint64_t m = std::min<uint64_t>(n, cap);
-    if (m) CUDA_TRY(ctx, cudaMemcpy(steps_out, dsteps.p, m * sizeof(GrrtStep), cudaMemcpyDeviceToHost));
+    if (m) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(steps_out, dsteps.p, m * sizeof(GrrtStep), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    }
     *n_out = n;
     *stop_reason = sr[0];
     return sr[1];  // GRRT_RAYERR_* (>0) of the ray, 0 when it integrated
@@ -813,15 +832,15 @@ int grrt_debug_pow(GrrtCtx* ctx, const double* x, const double* y, double* out, 
     if (!ctx || !x || !y || !out) return GRRT_ERR_INVALID_ARGUMENT;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     DevBuf dx, dy, dout;
-    CUDA_TRY(ctx, dx.alloc(n * 8));
-    CUDA_TRY(ctx, dy.alloc(n * 8));
-    CUDA_TRY(ctx, dout.alloc(n * 8));
-    CUDA_TRY(ctx, cudaMemcpy(dx.p, x, n * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(ctx, cudaMemcpy(dy.p, y, n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, dx.alloc(n * 8, ctx->stream));
+    CUDA_TRY(ctx, dy.alloc(n * 8, ctx->stream));
+    CUDA_TRY(ctx, dout.alloc(n * 8, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dx.p, x, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dy.p, y, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (n) debug_pow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dx.as<double>(), dy.as<double>(), dout.as<double>(), n);
     CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpy(out, dout.p, n * 8, cudaMemcpyDeviceToHost));
     return GRRT_OK;
 }
 
@@ -830,7 +849,7 @@ int grrt_measure_fp64_peak(GrrtCtx* ctx, double* dfma_per_second, double* ms_out
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const int blocks = ctx->num_sms * 8, threads = 256, iters = 20000;
     DevBuf out;
-    CUDA_TRY(ctx, out.alloc((size_t)blocks * threads * 8));
+    CUDA_TRY(ctx, out.alloc((size_t)blocks * threads * 8, ctx->stream));
     cudaEvent_t e0, e1;
     CUDA_TRY(ctx, cudaEventCreate(&e0));
     CUDA_TRY(ctx, cudaEventCreate(&e1));

@@ -57,7 +57,10 @@ class DeviceEngine:
         return None if t is None else C.c_void_p(t.data_ptr())
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # torch's default stream has handle 0, which the C ABI reads as "use the context's own stream":
+        # name the legacy default stream explicitly (cudaStreamLegacy == 0x1) so that work is ordered with torch's
+        h = torch.cuda.current_stream(self.device).cuda_stream
+        return C.c_void_p(h if h else 1)
 
     def trace(self, items, n_items, rect, spa, xyza, cls=None, stop=None, steps=None):
         self.ctx.trace_items_device(self.dscene, self._p(items), 0, n_items, rect, spa, self._p(xyza), self._p(cls),
