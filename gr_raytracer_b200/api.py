@@ -41,6 +41,7 @@ def lib():
     L.grrt_version.restype = C.c_char_p
     L.grrt_init.argtypes = [C.c_int, C.POINTER(vp)]
     L.grrt_destroy.argtypes = [vp]
+    L.grrt_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.grrt_kernel_launch_count.argtypes = [vp]
     L.grrt_kernel_launch_count.restype = C.c_ulonglong
     L.grrt_last_error.argtypes = [vp]
@@ -217,6 +218,9 @@ class Context:
         m_ = min(n.value, cap)
         dt = np.dtype([("x", "f8", 4), ("p", "f8", 4), ("t", "f8"), ("step", "u8")])
         return np.frombuffer(buf, dtype=dt, count=m_).copy(), stop.value, err
+
+    def set_option(self, name, value):
+        self._check(lib().grrt_set_option(self._h, name.encode(), int(value)))
 
     def launch_count(self):
         return int(lib().grrt_kernel_launch_count(self._h))

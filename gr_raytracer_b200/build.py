@@ -12,7 +12,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgrrt.so")
 CLI = os.path.join(HERE, "grrt")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CUDA_SOURCES = ["grrt_api.cu"]
+# (source, contract a*b+c into FMA?)  see csrc/grrt_kern_exact.cu / grrt_kern_fast.cu
+CUDA_SOURCES = ["grrt_api.cu", "grrt_kern_exact.cu", "grrt_kern_fast.cu"]
+FMAD = {"grrt_api.cu": "false", "grrt_kern_exact.cu": "false", "grrt_kern_fast.cu": "true"}
 HOST_SOURCES = ["host/toml.cpp", "host/png.cpp", "host/scene_build.cpp", "host/host_api.cpp"]
 CLI_SOURCES = ["host/cli_main.cpp"]
 
@@ -50,7 +52,7 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     common = ["-std=c++17", "-O3", "-lineinfo", "-ccbin", _host_cxx(), "-Xcompiler", "-fPIC", "-I", os.path.join(HERE, "..", "include")]
-    objs = []
+    objs, jobs = [], []
     for src in CUDA_SOURCES + [s for s in HOST_SOURCES if os.path.exists(os.path.join(CSRC, s))]:
         path = os.path.join(CSRC, src)
         obj = os.path.join(objdir, src.replace("/", "_") + ".o")
@@ -58,12 +60,25 @@ def build(force=False, verbose=False):
         if force or _newer(obj, deps):
             cmd = [nvcc] + ARCH + common + ["-c", path, "-o", obj]
             if src.endswith(".cu"):
-                cmd += ["-fmad=false", "-Xptxas", "-v"] if verbose else ["-fmad=false"]
+                cmd += ["-fmad=" + FMAD[src]] + (["-Xptxas", "-v"] if verbose else [])
             else:
                 cmd += ["-Xcompiler", "-ffp-contract=off"]
+            jobs.append(cmd)
+    if jobs:  # the translation units are independent: compile them concurrently
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             if verbose:
                 print(" ".join(cmd), flush=True)
-            subprocess.check_call(cmd)
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            return cmd, r.returncode, r.stdout
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 2)) as ex:
+            results = list(ex.map(run, jobs))
+        for cmd, rc, out in results:
+            if verbose or rc != 0:
+                print(out, flush=True)
+            if rc != 0:
+                raise subprocess.CalledProcessError(rc, cmd)
     if force or _newer(LIB, objs):
         cmd = [nvcc] + ARCH + ["-shared", "-ccbin", _host_cxx(), "-o", LIB] + objs + ["-lz", "-cudart", "static"]
         if verbose:

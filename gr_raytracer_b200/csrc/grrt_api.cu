@@ -5,6 +5,7 @@
 // GRRT_ERR_CUDA otherwise.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -12,7 +13,7 @@
 
 #include <cub/cub.cuh>
 
-#include "grrt_trace.cuh"
+#include "grrt_types.h"
 
 using namespace grrt;
 
@@ -27,6 +28,7 @@ struct GrrtCtx {
     void* d_cub_temp = nullptr;
     size_t cub_temp_bytes = 0;
     unsigned long long launches = 0;  // kernels of this library launched so far (bench.py's gpu_launches)
+    bool use_fma = true;              // smooth geometries: FMA-contracted kernels (GRRT_FMA=0 or grrt_set_option to disable)
 };
 
 struct GrrtDeviceScene {
@@ -153,6 +155,8 @@ __global__ void fill_mask_color_kernel(const uint32_t* sel, uint32_t n, const __
     d[0] = cfg.mask_xyza[0]; d[1] = cfg.mask_xyza[1]; d[2] = cfg.mask_xyza[2]; d[3] = cfg.mask_xyza[3];
 }
 
+__device__ __forceinline__ double rclamp(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
 // ---- tone mapping (color.rs:193-299) ----------------------------------------------------------------
 __device__ __forceinline__ void xyz_to_linear(const double* c, double out[3]) {
     out[0] = (3.2406255 * c[0] + -1.5372080 * c[1]) + -0.4986286 * c[2];
@@ -212,73 +216,6 @@ __global__ void tonemap_kernel(const double* xyza, size_t n, int method, double 
     for (int k = 0; k < 3; ++k) rgb[3 * i + k] = to_u8(compand_srgb(fmax(c[k], 0.0)) * 255.0);
 }
 
-// ---- single-ray trajectory export (integrator.rs:78-174 with every step stored) ---------------------
-template <int G>
-__global__ void trace_single_kernel(const __grid_constant__ DScene S, const double4 pos4, const double4 mom4,
-                                    int use_pixel, long long row, long long col, GrrtStep* steps,
-                                    unsigned long long cap, unsigned long long* n_out, int* stop_out, int* err_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double pos[4] = {pos4.x, pos4.y, pos4.z, pos4.w}, mom[4] = {mom4.x, mom4.y, mom4.z, mom4.w};
-    if (use_pixel) camera_ray<G>(S, (double)row, (double)col, pos, mom);
-    double y[8];
-    RayConst C;
-    RayCtx R;
-    init_ray<G>(S, pos, mom, y, C, R);
-    unsigned long long n = 0;
-    double t = 0.0;
-    auto store = [&](unsigned long long step) {
-        if (n < cap) {
-            double p[4];
-            momentum_from_state<G>(S, C, y, p);
-            for (int i = 0; i < 4; ++i) {
-                steps[n].x[i] = y[i];
-                steps[n].p[i] = p[i];
-            }
-            steps[n].t = t;
-            steps[n].step = step;
-        }
-        ++n;
-    };
-    store(0);
-    double h = S.step_size;
-    int stop = GRRT_STOP_NONE, error = 0;
-    for (unsigned long long i = 1; i < S.max_steps && !error; ++i) {
-        double h_cur = rclamp(h, kHMin, kHMax);
-        bool ok = false;
-        double y_new[8], err;
-        for (int r = 0; r < kMaxRetryStep; ++r) {
-            rkf45_step<G>(S, C, y, h_cur, y_new, err);
-            double h_proposed = err > 0.0 ? 0.9 * h_cur * pow_glibc(pow_tables_global(), S.epsilon / err, 1.0 / 5.0) : h_cur * kHGrowthCap;
-            h_proposed = rclamp(fmin(h_proposed, h_cur * kHGrowthCap), kHMin, kHMax);
-            if (err > S.epsilon) {
-                if (h_cur <= kHMin) {
-                    h = h_cur;
-                    ok = true;
-                    break;
-                }
-                h_cur = rclamp(h_proposed / 2.0, kHMin, kHMax);
-            } else {
-                h = (err / S.epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
-                ok = true;
-                break;
-            }
-        }
-        if (!ok) {
-            error = GRRT_RAYERR_RKF45_RETRIES;
-            stop = GRRT_STOP_ERROR;
-            break;
-        }
-        for (int k = 0; k < 8; ++k) y[k] = y_new[k];
-        t += h_cur;
-        store(i);
-        stop = should_stop<G>(S, y, position_cartesian<G>(S, y), i);
-        if (stop != GRRT_STOP_NONE) break;
-    }
-    *n_out = n;
-    *stop_out = stop;
-    *err_out = error;
-}
-
 // ---- FP64 issue-rate microbenchmark -----------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0,
@@ -293,39 +230,39 @@ __global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, int iters,
     out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
-__global__ void debug_pow_kernel(const double* x, const double* y, double* out, size_t n) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = pow_glibc(pow_tables_global(), x[i], y[i]);
-}
-
-// ---- launch helpers ---------------------------------------------------------------------------------
-template <int G, bool V>
-int launch_trace_t(GrrtCtx* ctx, const DScene& s, const TraceArgs& a, cudaStream_t st) {
-    int per_sm = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<G, V>, kTraceThreads, 0));
-    if (per_sm < 1) per_sm = 1;
-    unsigned long long want = (a.n_units + kTraceThreads - 1) / kTraceThreads;
-    unsigned long long grid = (unsigned long long)ctx->num_sms * per_sm;  // persistent: one wave, a multiple of the SM count
-    if (want < grid) grid = want;
-    if (grid == 0) return GRRT_OK;
-    trace_kernel<G, V><<<(unsigned)grid, kTraceThreads, 0, st>>>(s, a);
-    ++ctx->launches;
-    CUDA_TRY(ctx, cudaGetLastError());
-    return GRRT_OK;
-}
-template <bool V>
-int launch_trace_v(GrrtCtx* ctx, const DScene& s, const TraceArgs& a, cudaStream_t st) {
-    switch (s.geom) {
-        case GRRT_GEOM_EUCLIDEAN: return launch_trace_t<GRRT_GEOM_EUCLIDEAN, V>(ctx, s, a, st);
-        case GRRT_GEOM_EUCLIDEAN_SPHERICAL: return launch_trace_t<GRRT_GEOM_EUCLIDEAN_SPHERICAL, V>(ctx, s, a, st);
-        case GRRT_GEOM_SCHWARZSCHILD: return launch_trace_t<GRRT_GEOM_SCHWARZSCHILD, V>(ctx, s, a, st);
-        case GRRT_GEOM_KERR: return launch_trace_t<GRRT_GEOM_KERR, V>(ctx, s, a, st);
-        case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V>(ctx, s, a, st);
-        default: return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "unknown geometry kind");
+// mean over the valid sub-samples, summed in stratum order (raytracer.rs:341-379)
+__global__ void grrt_exact_resolve(const double* sub_xyza, const uint8_t* sub_valid, const uint32_t* items,
+                                   unsigned long long n_items, unsigned ss, double* xyza) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    double sx = 0.0, sy = 0.0, sz = 0.0, sa = 0.0;
+    unsigned valid = 0;
+    for (unsigned k = 0; k < ss; ++k) {
+        unsigned long long u = i * ss + k;
+        if (sub_valid[u]) {
+            const double* c = sub_xyza + 4 * u;
+            sx = sx + c[0]; sy = sy + c[1]; sz = sz + c[2]; sa = sa + c[3];
+            ++valid;
+        }
+    }
+    if (valid > 0) {
+        double inv = 1.0 / (double)valid;
+        double* dst = xyza + 4ull * items[i];
+        dst[0] = sx * inv; dst[1] = sy * inv; dst[2] = sz * inv; dst[3] = sa * inv;
     }
 }
+
 int launch_trace(GrrtCtx* ctx, const GrrtDeviceScene* ds, const TraceArgs& a, cudaStream_t st) {
-    return ds->has_vol ? launch_trace_v<true>(ctx, ds->s, a, st) : launch_trace_v<false>(ctx, ds->s, a, st);
+    TraceLaunch l{ctx->num_sms, st};
+    // Kerr-Schild always runs the exact (no-FMA) kernels; the smooth geometries use the FMA build unless disabled
+    const bool fast = ctx->use_fma && ds->s.geom != GRRT_GEOM_KERR;
+    int rc = fast ? grrt_fast::launch_trace(ds->s, a, ds->has_vol, l) : grrt_exact::launch_trace(ds->s, a, ds->has_vol, l);
+    if (rc != 0) {
+        ctx->last_error = std::string("trace_kernel launch: ") + cudaGetErrorString((cudaError_t)rc);
+        return GRRT_ERR_CUDA;
+    }
+    ++ctx->launches;
+    return GRRT_OK;
 }
 
 int ensure_cub_temp(GrrtCtx* ctx, size_t bytes) {
@@ -375,6 +312,7 @@ int grrt_init(int device_id, GrrtCtx** out) {
         return GRRT_ERR_CUDA;
     }
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char* e = std::getenv("GRRT_FMA")) ctx->use_fma = !(e[0] == '0');
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GRRT_ERR_CUDA; }
     {  // keep freed blocks cached in the device's default memory pool instead of returning them to the OS
         cudaMemPool_t pool;
@@ -405,6 +343,15 @@ void grrt_destroy(GrrtCtx* ctx) {
     if (ctx->d_cub_temp) cudaFree(ctx->d_cub_temp);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+int grrt_set_option(GrrtCtx* ctx, const char* name, int value) {
+    if (!ctx || !name) return GRRT_ERR_INVALID_ARGUMENT;
+    if (std::strcmp(name, "fma") == 0) {
+        ctx->use_fma = value != 0;
+        return GRRT_OK;
+    }
+    return GRRT_ERR_INVALID_ARGUMENT;
 }
 
 unsigned long long grrt_kernel_launch_count(const GrrtCtx* ctx) { return ctx ? ctx->launches : 0; }
@@ -578,7 +525,7 @@ int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint3
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned long long), st));
         int rc = launch_trace(ctx, ds, a, st);
         if (rc) return rc;
-        resolve_subsamples_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(sub.as<double>(), valid.as<uint8_t>(),
+        grrt_exact_resolve<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(sub.as<double>(), valid.as<uint8_t>(),
                                                                                 d_items + off, m, ss, d_xyza);
         ++ctx->launches;
         CUDA_TRY(ctx, cudaGetLastError());
@@ -780,27 +727,14 @@ static int trace_single(GrrtCtx* ctx, const GrrtScene* scene, const double* pos,
     DevBuf dsteps, meta;
     CUDA_TRY(ctx, dsteps.alloc(cap * sizeof(GrrtStep), ctx->stream));
     CUDA_TRY(ctx, meta.alloc(32, ctx->stream));
-    double4 p4 = make_double4(0, 0, 0, 0), m4 = make_double4(0, 0, 0, 0);
-    if (!use_pixel) {
-        p4 = make_double4(pos[0], pos[1], pos[2], pos[3]);
-        m4 = make_double4(mom[0], mom[1], mom[2], mom[3]);
-    }
     unsigned long long* d_n = meta.as<unsigned long long>();
     int* d_stop = reinterpret_cast<int*>(d_n + 1);
     int* d_err = d_stop + 1;
     cudaStream_t s = ctx->stream;
-#define LAUNCH_SINGLE(G)                                                                                          \
-    trace_single_kernel<G><<<1, 32, 0, s>>>(ds->s, p4, m4, use_pixel, (long long)row, (long long)col,            \
-                                            dsteps.as<GrrtStep>(), cap, d_n, d_stop, d_err)
-    switch (ds->s.geom) {
-        case GRRT_GEOM_EUCLIDEAN: LAUNCH_SINGLE(GRRT_GEOM_EUCLIDEAN); break;
-        case GRRT_GEOM_EUCLIDEAN_SPHERICAL: LAUNCH_SINGLE(GRRT_GEOM_EUCLIDEAN_SPHERICAL); break;
-        case GRRT_GEOM_SCHWARZSCHILD: LAUNCH_SINGLE(GRRT_GEOM_SCHWARZSCHILD); break;
-        case GRRT_GEOM_KERR: LAUNCH_SINGLE(GRRT_GEOM_KERR); break;
-        case GRRT_GEOM_KERR_BL: LAUNCH_SINGLE(GRRT_GEOM_KERR_BL); break;
-        default: return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "unknown geometry kind");
-    }
-#undef LAUNCH_SINGLE
+    int lrc = grrt_exact::launch_trace_single(ds->s, pos, mom, use_pixel, (long long)row, (long long)col, dsteps.as<GrrtStep>(), cap,
+                                              d_n, d_stop, d_err, s);
+    if (lrc != 0) return fail(ctx, GRRT_ERR_CUDA, std::string("trace_single launch: ") + cudaGetErrorString((cudaError_t)lrc));
+    ++ctx->launches;
     CUDA_TRY(ctx, cudaGetLastError());
     unsigned long long n = 0;
     int sr[2] = {0, 0};
@@ -837,8 +771,8 @@ int grrt_debug_pow(GrrtCtx* ctx, const double* x, const double* y, double* out, 
     CUDA_TRY(ctx, dout.alloc(n * 8, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(dx.p, x, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(dy.p, y, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (n) debug_pow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dx.as<double>(), dy.as<double>(), dout.as<double>(), n);
-    CUDA_TRY(ctx, cudaGetLastError());
+    if (grrt_exact::launch_debug_pow(dx.as<double>(), dy.as<double>(), dout.as<double>(), n, ctx->stream) != 0)
+        return fail(ctx, GRRT_ERR_CUDA, "debug_pow launch failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return GRRT_OK;

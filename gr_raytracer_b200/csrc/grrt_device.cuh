@@ -14,68 +14,21 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
-#include "../../include/grrt.h"
+#include "grrt_types.h"
 
-namespace grrt {
+// The same sources are compiled twice (see grrt_kern_exact.cu / grrt_kern_fast.cu): once without FMA contraction
+// (bit-parity with the reference) and once with it.  GRRT_NS keeps the two sets of symbols apart.
+#ifndef GRRT_NS
+#define GRRT_NS grrt_exact
+#endif
+
+namespace GRRT_NS {
+using namespace grrt;
 
 #define GD __device__ __forceinline__
 #define GDN __device__ __noinline__
 
 constexpr double kPi = 3.14159265358979323846;
-
-// ---- device scene (kernel parameter block; lives in the constant bank) ------------------
-struct DTexture {
-    int kind;
-    uint32_t width, height;
-    double beaming;
-    const uint8_t* rgba;
-    double cw, ch;
-    double c1[4], c2[4];
-};
-struct DTemperature {
-    int kind;
-    uint32_t n;
-    double constant, r_isco;
-    const double* lut_r;
-    const double* lut_t;
-};
-struct DObject {
-    int kind;
-    int perm_slot;  // index into the shared-memory Perlin tables
-    DTexture tex;
-    DTemperature temp;
-    double radius, pos[3], sphere_temperature;
-    double r_in, r_out;
-    double axis[3], e1[3], e2[3];
-    uint64_t num_octaves, vol_max_steps;
-    double vol_step, thickness, density_multiplier, bref_temperature, absorption, scattering;
-    double noise_scale[3], noise_offset;
-    const uint8_t* perm;
-};
-struct DScene {
-    int geom;
-    int kerr_mode;
-    double radius, a, heps;
-    double r_plus_eps;      // horizon radius + epsilon (Kerr / KerrBL), precomputed as the reference does per call
-    int horizon_enabled;
-    int n_objects;
-    // camera
-    double cam_pos[4], cam_vel[4], tet[4][4];
-    double cam_scale;       // 2 tan(alpha/2) / rows
-    double cam_rows, cam_cols, cam_hand, cam_sig;
-    // integration
-    uint64_t max_steps;
-    double max_radius_sq, step_size, epsilon;
-    double hit_opacity_threshold;
-    DTexture celestial;
-    double celestial_temperature;
-    const double* bb_log_t;
-    const double* bb_xyz;
-    uint32_t bb_n;
-    uint32_t n_vol;          // number of VolumetricDisc objects
-    const double* srgb_lut;  // 256 entries: inv_compand_srgb(i/255) (color.rs:301-308), built on the host
-    DObject obj[GRRT_MAX_OBJECTS];
-};
 
 struct Cie {
     double x, y, z, a;
@@ -959,4 +912,4 @@ GD double hash_pixel_samples(long long row, long long col, unsigned long long k)
     return (double)(z >> 11) * (1.0 / 9007199254740992.0);
 }
 
-}  // namespace grrt
+}  // namespace GRRT_NS

@@ -7,6 +7,16 @@
 // the 100x spread in steps-per-ray (171 ... 15 500 ... 276 733) never idles a lane; only the
 // rare per-ray events (ray set-up, object shading, terminal colour) diverge.
 //
+// RKF45 attempt (v2): the six stages run as a real loop -- one copy of the right-hand side in the
+// instruction stream, ~300 SASS instructions per trip -- instead of six inlined copies (v1 was
+// 12.6k instructions for KerrBL and spent 1.4 stall cycles per issue waiting for instruction
+// fetch, profiles/r1_c2_trace_kernel_v1.json).  The stage derivatives k1..k5 live in shared memory
+// ([stage][component][thread], conflict-free), the 5th-order solution and the error vector are
+// accumulated in registers as each stage completes -- the same left-to-right order in which
+// runge_kutta.rs:115-123 sums them.  State components whose derivative is identically zero
+// (KerrBL: 6,7; Kerr-Schild: p_t; flat Cartesian: all momenta) are skipped: they contribute exact
+// zeros to every sum of the reference, so nothing changes numerically.
+//
 // The reference stores the whole trajectory (112 B per step) and walks it a second time
 // (scene.rs:141-152); here each accepted step is tested against the objects as it is produced
 // and only the previous state is kept (in shared memory: it is read only when a hit occurs).
@@ -21,32 +31,35 @@
 #include "grrt_device.cuh"
 #include "grrt_pow.cuh"
 
-namespace grrt {
+namespace GRRT_NS {
 
-constexpr int kTraceThreads = 128;
 constexpr int kMaxHits = 32;
 constexpr int kMaxRetryStep = 100;  // runge_kutta.rs:60
 constexpr unsigned kFull = 0xffffffffu;
 
-enum { CNT_ATTEMPTS = 0, CNT_ACCEPTED = 1, CNT_SAMPLES = 2, CNT_ERRORS = 3, CNT_OVERFLOW = 4, CNT_RAYS = 5,
-       CNT_STOP0 = 8 /* 8..13 */ };
+// Fehlberg tableau as data for the stage loop (same expressions as the RK_* constants)
+__constant__ double c_rk_b[6][5] = {
+    {0.0, 0.0, 0.0, 0.0, 0.0},
+    {RK_B21, 0.0, 0.0, 0.0, 0.0},
+    {RK_B31, RK_B32, 0.0, 0.0, 0.0},
+    {RK_B41, RK_B42, RK_B43, 0.0, 0.0},
+    {RK_B51, RK_B52, RK_B53, RK_B54, 0.0},
+    {RK_B61, RK_B62, RK_B63, RK_B64, RK_B65}};
+__constant__ double c_rk_ch[6] = {RK_CH1, RK_CH2, RK_CH3, RK_CH4, RK_CH5, RK_CH6};
+__constant__ double c_rk_ct[6] = {RK_CT1, RK_CT2, RK_CT3, RK_CT4, RK_CT5, RK_CT6};
 
-struct TraceArgs {
-    const uint32_t* items;      // nullable: pixel ids (row-major within the rectangle)
-    unsigned long long first_item;
-    unsigned long long n_items;
-    unsigned long long n_units;  // work units handed out by the queue
-    uint32_t from_row, from_col, width, height;
-    uint32_t spa;                // 0: centre ray per item;  N: N*N stratified sub-samples per item
-    uint32_t tiled;              // items == NULL && spa == 0: units enumerate 8x4 pixel tiles
-    uint32_t tiles_x;
-    double* xyza;                // spa == 0: per item;  spa > 0: per unit
-    uint8_t* cls;
-    uint8_t* stop;
-    uint32_t* steps;
-    uint8_t* sub_valid;          // spa > 0: per unit
-    unsigned long long* queue;
-    unsigned long long* counters;
+// which of the 8 state components have a non-zero derivative
+template <int G>
+struct Comp {
+    __host__ __device__ static constexpr bool on(int i) {
+        return G == GRRT_GEOM_EUCLIDEAN ? i < 4 : (G == GRRT_GEOM_KERR_BL ? i < 6 : (G == GRRT_GEOM_KERR ? i != 4 : true));
+    }
+    __host__ __device__ static constexpr int slot(int i) {  // dense index of an active component
+        int n = 0;
+        for (int j = 0; j < i; ++j) n += on(j) ? 1 : 0;
+        return n;
+    }
+    static constexpr int count = slot(8);
 };
 
 struct RayCtx {  // per-lane ray bookkeeping that is not touched inside an attempt
@@ -251,12 +264,21 @@ __device__ __noinline__ Cie vol_march_warp(const DScene& S, const DObject& o, co
 enum { ST_IDLE = 0, ST_ACTIVE = 1, ST_DEAD = 2 };
 
 template <int G, bool HAS_VOL>
-__global__ void __launch_bounds__(kTraceThreads)
+constexpr size_t trace_smem_bytes() {
+    return sizeof(double) * (size_t)(5 * Comp<G>::count + 8) * kTraceThreads + sizeof(double) * 128 * 3 + 8 * 256 +
+           (HAS_VOL ? GRRT_MAX_OBJECTS * 256 : 0);
+}
+
+template <int G, bool HAS_VOL, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kTraceThreads, MIN_BLOCKS)
 trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs A) {
-    __shared__ double s_yprev[8][kTraceThreads];
-    __shared__ uint8_t s_perm[HAS_VOL ? GRRT_MAX_OBJECTS : 1][256];
-    __shared__ double s_pow_log[128][3];           // glibc-compatible pow tables (grrt_pow.cuh): divergent lookups
-    __shared__ unsigned long long s_pow_exp[256];
+    constexpr int NC = Comp<G>::count;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_k = reinterpret_cast<double*>(smem_raw);                       // [5][NC][threads]
+    double* s_yprev = s_k + 5 * NC * kTraceThreads;                          // [8][threads]
+    double (*s_pow_log)[3] = reinterpret_cast<double (*)[3]>(s_yprev + 8 * kTraceThreads);  // glibc-compatible pow tables
+    unsigned long long* s_pow_exp = reinterpret_cast<unsigned long long*>(s_pow_log + 128);
+    uint8_t* s_perm = reinterpret_cast<uint8_t*>(s_pow_exp + 256);           // [n_vol][256]
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     for (int i = tid; i < 128 * 3; i += kTraceThreads) (&s_pow_log[0][0])[i] = (&kPowLogTab[0][0])[i];
@@ -267,12 +289,14 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
     if (HAS_VOL) {
         for (int k = 0; k < S.n_objects; ++k)
             if (S.obj[k].kind == GRRT_OBJ_VOLUMETRIC_DISC)
-                for (int i = tid; i < 256; i += kTraceThreads) s_perm[S.obj[k].perm_slot][i] = S.obj[k].perm[i];
+                for (int i = tid; i < 256; i += kTraceThreads) s_perm[S.obj[k].perm_slot * 256 + i] = S.obj[k].perm[i];
     }
     __syncthreads();
 
     int state = ST_IDLE;
     double y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = 0.0;
     double h = 0.0, h_cur = 0.0;
     RayConst C = {0.0, 0.0, 0.0};
     RayCtx R;
@@ -351,12 +375,50 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
         bool budget_empty = active && (S.max_steps <= 1);  // `for i in 1..max_steps` runs zero times
         if (budget_empty) finish = GRRT_STOP_NONE;
 
-        // ---------------- one RKF45 attempt (runge_kutta.rs:138-182, flattened retry loop) ----------------
+        // ---------------- one RKF45 attempt (runge_kutta.rs:86-182, flattened retry loop) ----------------
         double y_new[8];
-        double err = 0.0;
         bool accepted = false;
         if (active && !budget_empty) {
-            rkf45_step<G>(S, C, y, h_cur, y_new, err);
+            double acc_e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                y_new[i] = y[i];
+                acc_e[i] = 0.0;
+            }
+#pragma unroll 1
+            for (int s = 0; s < 6; ++s) {
+                double tmp[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tmp[i] = y[i];
+#pragma unroll 1
+                for (int j = 0; j < s; ++j) {  // y + B_s1 k1 + B_s2 k2 + ... left to right
+                    const double b = c_rk_b[s][j];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (Comp<G>::on(i)) tmp[i] = tmp[i] + b * s_k[(j * NC + Comp<G>::slot(i)) * kTraceThreads + tid];
+                }
+                double d[8];
+                geodesic_rhs<G>(S, C, tmp, d);
+                const double ch = c_rk_ch[s], ct = c_rk_ct[s];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (Comp<G>::on(i)) {
+                        const double k = h_cur * d[i];
+                        if (s < 5) s_k[(s * NC + Comp<G>::slot(i)) * kTraceThreads + tid] = k;
+                        y_new[i] = y_new[i] + ch * k;
+                        acc_e[i] = acc_e[i] + ct * k;
+                    }
+                }
+            }
+            // truncation error: nalgebra's 8-accumulator dot product, (0,4) (1,5) (2,6) (3,7)
+            double e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = Comp<G>::on(i) ? acc_e[i] * acc_e[i] : 0.0;
+            double res = (e[0] + e[4]);
+            res = res + (e[1] + e[5]);
+            res = res + (e[2] + e[6]);
+            res = res + (e[3] + e[7]);
+            const double err = sqrt(res);
             ++ray_attempts;
             double h_proposed;
             if (err > 0.0) h_proposed = 0.9 * h_cur * pow_glibc(pow_tab, S.epsilon / err, 1.0 / 5.0);
@@ -378,7 +440,6 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 h = (err / S.epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
             }
         }
-
         // ---------------- accepted step: objects on the chord prev -> cur ----------------
         V3 cart = v3(0.0, 0.0, 0.0);
         bool have_hit = false;
@@ -389,7 +450,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
         Cie hit_color = cie(0.0, 0.0, 0.0, 0.0);
         if (accepted) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) s_yprev[i][tid] = y[i];
+            for (int i = 0; i < 8; ++i) s_yprev[i * kTraceThreads + tid] = y[i];
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = y_new[i];
             ++R.step;
@@ -414,7 +475,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 // step_at_intersection (objects.rs:27-44): exact point, lerped momentum
                 double yp[8], p0[4], p1[4], xs[4], ps[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i][tid];
+                for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i * kTraceThreads + tid];
                 momentum_from_state<G>(S, C, yp, p0);
                 momentum_from_state<G>(S, C, y, p1);
                 double s = 1.0 - hcur.t;
@@ -474,7 +535,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 int merr = 0;
                 unsigned long long smp = 0;
                 const DObject& o = S.obj[k];
-                Cie c = vol_march_warp<G>(S, o, s_perm[o.perm_slot], ro, rd, fe, fpt, fpp, &merr, &smp);
+                Cie c = vol_march_warp<G>(S, o, s_perm + o.perm_slot * 256, ro, rd, fe, fpt, fpp, &merr, &smp);
                 if (lane == src) {
                     hit_color = c;  // a failed march yields (0,0,0,0) (volumetric_disc.rs:596-600)
                     c_samples += smp;
@@ -572,26 +633,23 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
     }
 }
 
-// mean over the valid sub-samples, summed in stratum order (raytracer.rs:341-379)
-__global__ void resolve_subsamples_kernel(const double* sub_xyza, const uint8_t* sub_valid, const uint32_t* items,
-                                          unsigned long long n_items, unsigned ss, double* xyza) {
-    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i >= n_items) return;
-    double sx = 0.0, sy = 0.0, sz = 0.0, sa = 0.0;
-    unsigned valid = 0;
-    for (unsigned k = 0; k < ss; ++k) {
-        unsigned long long u = i * ss + k;
-        if (sub_valid[u]) {
-            const double* c = sub_xyza + 4 * u;
-            sx = sx + c[0]; sy = sy + c[1]; sz = sz + c[2]; sa = sa + c[3];
-            ++valid;
-        }
-    }
-    if (valid > 0) {
-        double inv = 1.0 / (double)valid;
-        double* dst = xyza + 4ull * items[i];
-        dst[0] = sx * inv; dst[1] = sy * inv; dst[2] = sz * inv; dst[3] = sa * inv;
-    }
-}
 
-}  // namespace grrt
+// ---- launch ---------------------------------------------------------------------------------------------
+template <int G, bool V, int MB>
+int launch_trace_t(const DScene& s, const TraceArgs& a, const TraceLaunch& l) {
+    auto kern = trace_kernel<G, V, MB>;
+    const size_t smem = trace_smem_bytes<G, V>();
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTraceThreads, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long want = (a.n_units + kTraceThreads - 1) / kTraceThreads;
+    unsigned long long grid = (unsigned long long)l.num_sms * per_sm;  // persistent: one wave, a multiple of the SM count
+    if (want < grid) grid = want;
+    if (grid == 0) return 0;
+    kern<<<(unsigned)grid, kTraceThreads, smem, l.stream>>>(s, a);
+    return (int)cudaGetLastError();
+}
+}  // namespace GRRT_NS

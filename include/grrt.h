@@ -238,6 +238,10 @@ int grrt_init(int device_id, GrrtCtx** out);
 void grrt_destroy(GrrtCtx* ctx);
 const char* grrt_last_error(const GrrtCtx* ctx);
 const char* grrt_version(void);
+/* Options: "fma" (default 1): the smooth geometries (Euclidean, EuclideanSpherical, Schwarzschild, KerrBL) run kernels
+ * compiled with FMA contraction; 0 selects the contraction-free kernels for every geometry (Kerr-Schild always
+ * uses those).  Environment variable GRRT_FMA=0 has the same effect at grrt_init. */
+int grrt_set_option(GrrtCtx* ctx, const char* name, int value);
 /* Number of this library's own kernels launched through `ctx` so far (CUB/memset launches not counted). */
 unsigned long long grrt_kernel_launch_count(const GrrtCtx* ctx);
 
