@@ -66,6 +66,21 @@ GD unsigned long long sat_u64(double x) {
     return (unsigned long long)x;
 }
 
+#ifdef GRRT_FAST_MATH
+// 1/x for the FMA build: hardware seed (rel. error 2^-23) + two Newton steps; ~1 ulp, no branches, 5 instructions
+// instead of the ~14 (plus a slow-path call) of an IEEE division.  Only used where the divisor is a well-scaled
+// positive/finite quantity of the right-hand sides (r, Delta, sin(theta), 1 - r_s/r).
+GD double frcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+#endif
+
 // ---- Kerr-Schild metric pieces (kerr.rs:31-110) -------------------------------------------
 GD double ks_r_sqr(double a, double x, double y, double z) {
     double rho_sqr = x * x + y * y + z * z;
@@ -328,6 +343,29 @@ GD void geodesic_rhs(const DScene& S, const RayConst& C, const double* y, double
         double v_t = y[4], v_r = y[5], v_theta = y[6], v_phi = y[7];
         double s, c;
         sincos(y[2], &s, &c);
+#ifdef GRRT_FAST_MATH
+        {   // same formulas with shared reciprocals (3 instead of 5-6 divisions)
+            const double inv_r = frcp(r), inv_s = frcp(s);
+            double a_t = 0.0, a_r;
+            const double sph = v_theta * v_theta + v_phi * v_phi * s * s;
+            if (G == GRRT_GEOM_SCHWARZSCHILD) {
+                const double rr = S.radius * inv_r;
+                const double a = 1.0 - rr;
+                const double a_prime = rr * inv_r;
+                const double apa = a_prime * frcp(a);
+                a_t = -apa * v_t * v_r;
+                a_r = -0.5 * a * a_prime * v_t * v_t + 0.5 * apa * v_r * v_r + a * r * sph;
+            } else {
+                a_r = r * sph;
+            }
+            const double two_over_r = 2.0 * inv_r;
+            d[0] = v_t; d[1] = v_r; d[2] = v_theta; d[3] = v_phi;
+            d[4] = a_t; d[5] = a_r;
+            d[6] = -two_over_r * v_r * v_theta + s * c * v_phi * v_phi;
+            d[7] = -two_over_r * v_phi * v_r - 2.0 * c * inv_s * v_theta * v_phi;
+            return;
+        }
+#endif
         double a_t, a_r;
         if (G == GRRT_GEOM_SCHWARZSCHILD) {
             double a = 1.0 - S.radius / r;
@@ -354,6 +392,23 @@ GD void geodesic_rhs(const DScene& S, const RayConst& C, const double* y, double
         double rr_aa = r * r + a * a;
         double p_r = rr_aa * C.e - a * C.l_z;
         double sin2 = sin_t * sin_t;
+#ifdef GRRT_FAST_MATH
+        {   // same formulas with two shared reciprocals (1/Delta, 1/sin) instead of five divisions
+            const double t1 = p_r * frcp(del);
+            const double inv_s = frcp(sin_t), inv_s2 = inv_s * inv_s;
+            const double ae = a * C.e;
+            const double lae = C.l_z - ae;
+            const double carter = lae * lae + C.q;
+            d[0] = rr_aa * t1 + a * (C.l_z - ae * sin2);
+            d[1] = v_r;
+            d[2] = v_theta;
+            d[3] = a * t1 + C.l_z * inv_s2 - ae;
+            d[4] = 2.0 * r * C.e * p_r - (r - 0.5 * r_s) * carter;
+            d[5] = cos_t * (C.l_z * C.l_z * inv_s2 * inv_s - ae * ae * sin_t);
+            d[6] = 0.0; d[7] = 0.0;
+            return;
+        }
+#endif
         double dt = rr_aa / del * p_r + a * (C.l_z - a * C.e * sin2);
         double dphi = a / del * p_r + C.l_z / sin2 - a * C.e;
         double lae = C.l_z - a * C.e;

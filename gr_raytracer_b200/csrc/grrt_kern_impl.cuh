@@ -5,6 +5,10 @@
 
 #include "grrt_trace.cuh"
 
+#ifndef GRRT_MB
+#define GRRT_MB 4  // resident CTAs per SM the register allocator is asked to allow for the non-volumetric kernels
+#endif
+
 namespace GRRT_NS {
 
 template <bool V>
@@ -12,8 +16,8 @@ int launch_trace_v(const DScene& s, const TraceArgs& a, const TraceLaunch& l) {
     switch (s.geom) {
         case GRRT_GEOM_EUCLIDEAN: return launch_trace_t<GRRT_GEOM_EUCLIDEAN, V, 3>(s, a, l);
         case GRRT_GEOM_EUCLIDEAN_SPHERICAL: return launch_trace_t<GRRT_GEOM_EUCLIDEAN_SPHERICAL, V, 3>(s, a, l);
-        case GRRT_GEOM_SCHWARZSCHILD: return launch_trace_t<GRRT_GEOM_SCHWARZSCHILD, V, 3>(s, a, l);
-        case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V, 3>(s, a, l);
+        case GRRT_GEOM_SCHWARZSCHILD: return launch_trace_t<GRRT_GEOM_SCHWARZSCHILD, V, (V ? 3 : GRRT_MB)>(s, a, l);
+        case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V, (V ? 3 : GRRT_MB)>(s, a, l);
 #ifdef GRRT_WITH_KERR_SCHILD
         case GRRT_GEOM_KERR: return launch_trace_t<GRRT_GEOM_KERR, V, 2>(s, a, l);
 #endif
@@ -36,8 +40,8 @@ __global__ void trace_single_kernel(const __grid_constant__ DScene S, const doub
     if (use_pixel) camera_ray<G>(S, (double)row, (double)col, pos, mom);
     double y[8];
     RayConst C;
-    RayCtx R;
-    init_ray<G>(S, pos, mom, y, C, R);
+    Freq F;
+    init_ray<G>(S, pos, mom, y, C, F);
     unsigned long long n = 0;
     double t = 0.0;
     auto store = [&](unsigned long long step) {

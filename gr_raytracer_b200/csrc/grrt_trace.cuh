@@ -62,14 +62,18 @@ struct Comp {
     static constexpr int count = slot(8);
 };
 
-struct RayCtx {  // per-lane ray bookkeeping that is not touched inside an attempt
-    double freq_e, freq_pt, freq_pphi;
-    V3 prev_cart;
-    double opacity;
+struct RayCtx {  // per-lane ray bookkeeping kept in registers
     unsigned long long unit;
-    unsigned long long step;
+    unsigned step;
+    unsigned attempts;
     int n_hits;
     int retries;
+};
+// ... and the part that is only touched at accepted steps / hits / ray end, kept in shared memory
+// ([slot][thread], conflict-free) so that the RKF45 stage loop has the registers to itself
+enum { CX_FREQ_E = 0, CX_FREQ_PT = 1, CX_FREQ_PPHI = 2, CX_OPACITY = 3, CX_PREV_X = 4, CX_PREV_Y = 5, CX_PREV_Z = 6, CX_SLOTS = 7 };
+struct Freq {
+    double e, pt, pphi;
 };
 
 template <int G>
@@ -91,7 +95,7 @@ GD void camera_ray(const DScene& S, double row, double column, double pos[4], do
 
 // get_geodesic_solver + create_initial_state + get_ray_frequency_data
 template <int G>
-GD void init_ray(const DScene& S, const double pos[4], const double mom[4], double y[8], RayConst& C, RayCtx& R) {
+GD void init_ray(const DScene& S, const double pos[4], const double mom[4], double y[8], RayConst& C, Freq& F) {
     C.e = C.l_z = C.q = 0.0;
     if (G == GRRT_GEOM_KERR_BL) {  // kerr_bl.rs:505-577 (BL branch), 176-223
         double r = pos[1];
@@ -138,9 +142,9 @@ GD void init_ray(const DScene& S, const double pos[4], const double mom[4], doub
     if (GeomTraits<G>::chart == CH_CART) {
         axial[1] = -pos[2]; axial[2] = pos[1]; axial[3] = 0.0;
     }
-    R.freq_e = inner_product<G>(S, pos, S.cam_vel, mom);
-    R.freq_pt = inner_product<G>(S, pos, e_t, mom);
-    R.freq_pphi = inner_product<G>(S, pos, axial, mom);
+    F.e = inner_product<G>(S, pos, S.cam_vel, mom);
+    F.pt = inner_product<G>(S, pos, e_t, mom);
+    F.pphi = inner_product<G>(S, pos, axial, mom);
 }
 
 // ---- warp-cooperative VolumetricDisc ray-march (volumetric_disc.rs:209-328) --------------------------
@@ -265,7 +269,7 @@ enum { ST_IDLE = 0, ST_ACTIVE = 1, ST_DEAD = 2 };
 
 template <int G, bool HAS_VOL>
 constexpr size_t trace_smem_bytes() {
-    return sizeof(double) * (size_t)(5 * Comp<G>::count + 8) * kTraceThreads + sizeof(double) * 128 * 3 + 8 * 256 +
+    return sizeof(double) * (size_t)(5 * Comp<G>::count + 8 + CX_SLOTS) * kTraceThreads + sizeof(double) * 128 * 3 + 8 * 256 +
            (HAS_VOL ? GRRT_MAX_OBJECTS * 256 : 0);
 }
 
@@ -276,7 +280,8 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_k = reinterpret_cast<double*>(smem_raw);                       // [5][NC][threads]
     double* s_yprev = s_k + 5 * NC * kTraceThreads;                          // [8][threads]
-    double (*s_pow_log)[3] = reinterpret_cast<double (*)[3]>(s_yprev + 8 * kTraceThreads);  // glibc-compatible pow tables
+    double* s_ctx = s_yprev + 8 * kTraceThreads;                             // [CX_SLOTS][threads]
+    double (*s_pow_log)[3] = reinterpret_cast<double (*)[3]>(s_ctx + CX_SLOTS * kTraceThreads);  // glibc-compatible pow tables
     unsigned long long* s_pow_exp = reinterpret_cast<unsigned long long*>(s_pow_log + 128);
     uint8_t* s_perm = reinterpret_cast<uint8_t*>(s_pow_exp + 256);           // [n_vol][256]
     const int tid = threadIdx.x;
@@ -300,12 +305,9 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
     double h = 0.0, h_cur = 0.0;
     RayConst C = {0.0, 0.0, 0.0};
     RayCtx R;
-    R.n_hits = 0; R.retries = 0; R.opacity = 0.0; R.unit = 0; R.step = 0;
-    R.freq_e = R.freq_pt = R.freq_pphi = 0.0;
-    R.prev_cart = v3(0.0, 0.0, 0.0);
+    R.n_hits = 0; R.retries = 0; R.unit = 0; R.step = 0; R.attempts = 0;
+#define CTX(slot) s_ctx[(slot) * kTraceThreads + tid]
     Cie hits[kMaxHits];
-    unsigned long long c_attempts = 0, c_accepted = 0, c_samples = 0, c_errors = 0, c_overflow = 0, c_rays = 0;
-    unsigned long long ray_attempts = 0;
     const unsigned ss = A.spa ? A.spa * A.spa : 1u;
 
     for (;;) {
@@ -351,18 +353,24 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                         }
                         double pos[4], mom[4];
                         camera_ray<G>(S, frow, fcol, pos, mom);
-                        init_ray<G>(S, pos, mom, y, C, R);
+                        Freq F;
+                        init_ray<G>(S, pos, mom, y, C, F);
+                        CTX(CX_FREQ_E) = F.e;
+                        CTX(CX_FREQ_PT) = F.pt;
+                        CTX(CX_FREQ_PPHI) = F.pphi;
+                        CTX(CX_OPACITY) = 0.0;
+                        const V3 c0 = position_cartesian<G>(S, y);
+                        CTX(CX_PREV_X) = c0.x;
+                        CTX(CX_PREV_Y) = c0.y;
+                        CTX(CX_PREV_Z) = c0.z;
                         R.unit = A.tiled ? item : unit;
                         R.step = 0;
+                        R.attempts = 0;
                         R.n_hits = 0;
                         R.retries = 0;
-                        R.opacity = 0.0;
-                        R.prev_cart = position_cartesian<G>(S, y);
                         h = S.step_size;
                         h_cur = rclamp(h, kHMin, kHMax);
-                        ray_attempts = 0;
                         state = ST_ACTIVE;
-                        ++c_rays;
                     }
                 }
             }
@@ -419,7 +427,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
             res = res + (e[2] + e[6]);
             res = res + (e[3] + e[7]);
             const double err = sqrt(res);
-            ++ray_attempts;
+            ++R.attempts;
             double h_proposed;
             if (err > 0.0) h_proposed = 0.9 * h_cur * pow_glibc(pow_tab, S.epsilon / err, 1.0 / 5.0);
             else h_proposed = h_cur * kHGrowthCap;
@@ -457,6 +465,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
             R.retries = 0;
             h_cur = rclamp(h, kHMin, kHMax);
             cart = position_cartesian<G>(S, y);
+            const V3 prev_cart = v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z));
             // Objects::intersects (objects.rs:65-120)
             double shortest = 1.7976931348623157e308;
             int best_k = -1;
@@ -465,11 +474,11 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 const DObject& o = S.obj[k];
                 Hit hcur;
                 bool hit;
-                if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, R.prev_cart, cart, hcur);
-                else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, R.prev_cart, cart, hcur);
-                else hit = vol_intersects(o, R.prev_cart, cart, hcur);
+                if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
+                else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
+                else hit = vol_intersects(o, prev_cart, cart, hcur);
                 if (!hit) continue;
-                double distance = norm3(hcur.point - R.prev_cart);
+                double distance = norm3(hcur.point - prev_cart);
                 if (!(distance < shortest)) continue;
                 shortest = distance;
                 // step_at_intersection (objects.rs:27-44): exact point, lerped momentum
@@ -491,7 +500,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                     break;
                 }
                 double emitter_energy = inner_product<G>(S, xs, vel, ps);
-                best_redshift = (GeomTraits<G>::sig0 * R.freq_e) / (GeomTraits<G>::sig0 * emitter_energy);
+                best_redshift = (GeomTraits<G>::sig0 * CTX(CX_FREQ_E)) / (GeomTraits<G>::sig0 * emitter_energy);
                 if (o.kind == GRRT_OBJ_SPHERE) {
                     best_temperature = o.sphere_temperature;
                 } else {
@@ -529,16 +538,17 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 dir.y = __shfl_sync(kFull, best.dir.y, src);
                 dir.z = __shfl_sync(kFull, best.dir.z, src);
                 rd = dir / norm3(dir);  // .normalize() (volumetric_disc.rs:589-594)
-                const double fe = __shfl_sync(kFull, R.freq_e, src);
-                const double fpt = __shfl_sync(kFull, R.freq_pt, src);
-                const double fpp = __shfl_sync(kFull, R.freq_pphi, src);
+                const int src_tid = (tid & ~31) | src;
+                const double fe = s_ctx[CX_FREQ_E * kTraceThreads + src_tid];
+                const double fpt = s_ctx[CX_FREQ_PT * kTraceThreads + src_tid];
+                const double fpp = s_ctx[CX_FREQ_PPHI * kTraceThreads + src_tid];
                 int merr = 0;
                 unsigned long long smp = 0;
                 const DObject& o = S.obj[k];
                 Cie c = vol_march_warp<G>(S, o, s_perm + o.perm_slot * 256, ro, rd, fe, fpt, fpp, &merr, &smp);
                 if (lane == src) {
                     hit_color = c;  // a failed march yields (0,0,0,0) (volumetric_disc.rs:596-600)
-                    c_samples += smp;
+                    if (A.counters) atomicAdd(A.counters + CNT_SAMPLES, smp);
                 }
             }
         }
@@ -550,12 +560,14 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                     hits[R.n_hits++] = hit_color;
                 } else {  // fold into the last slot: "older over newer" keeps the compositing order
                     hits[kMaxHits - 1] = blend(hit_color, hits[kMaxHits - 1]);
-                    ++c_overflow;
+                    if (A.counters) atomicAdd(A.counters + CNT_OVERFLOW, 1ull);
                 }
                 double alpha = rclamp(hit_color.a, 0.0, 1.0);
-                R.opacity = alpha + R.opacity * (1.0 - alpha);  // scene.rs:149-150
+                CTX(CX_OPACITY) = alpha + CTX(CX_OPACITY) * (1.0 - alpha);  // scene.rs:149-150
             }
-            R.prev_cart = cart;
+            CTX(CX_PREV_X) = cart.x;
+            CTX(CX_PREV_Y) = cart.y;
+            CTX(CX_PREV_Z) = cart.z;
             int st = should_stop<G>(S, y, cart, R.step);
             if (st != GRRT_STOP_NONE) finish = st;
             else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
@@ -588,7 +600,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                     stationary_velocity<G>(S, y, vel);
                     momentum_from_state<G>(S, C, y, p);
                     double emitter_energy = inner_product<G>(S, y, vel, p);
-                    double redshift = (GeomTraits<G>::sig0 * R.freq_e) / (GeomTraits<G>::sig0 * emitter_energy);
+                    double redshift = (GeomTraits<G>::sig0 * CTX(CX_FREQ_E)) / (GeomTraits<G>::sig0 * emitter_energy);
                     terminal = texture_color(S, S.celestial, 1.0 - u, v, S.celestial_temperature, redshift);
                     has_terminal = true;
                     ray_class = GRRT_CLASS_ESCAPED;
@@ -597,9 +609,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 }
                 if (has_terminal) result = blend(result, terminal);
                 for (int k = R.n_hits - 1; k >= 0; --k) result = blend(result, hits[k]);
-                if (R.opacity >= S.hit_opacity_threshold) ray_class = GRRT_CLASS_HIT;
-            } else {
-                ++c_errors;
+                if (CTX(CX_OPACITY) >= S.hit_opacity_threshold) ray_class = GRRT_CLASS_HIT;
             }
             // write out
             const unsigned long long o = R.unit;
@@ -614,25 +624,19 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 dst[0] = result.x; dst[1] = result.y; dst[2] = result.z; dst[3] = result.a;
                 A.sub_valid[o] = finish != GRRT_STOP_ERROR ? 1 : 0;
             }
-            c_attempts += ray_attempts;
-            c_accepted += R.step;
-            if (A.counters) atomicAdd(A.counters + CNT_STOP0 + finish, 1ull);
+            if (A.counters) {  // once per ray: negligible next to the thousands of attempts a ray takes
+                atomicAdd(A.counters + CNT_ATTEMPTS, (unsigned long long)R.attempts);
+                atomicAdd(A.counters + CNT_ACCEPTED, (unsigned long long)R.step);
+                atomicAdd(A.counters + CNT_RAYS, 1ull);
+                atomicAdd(A.counters + CNT_STOP0 + finish, 1ull);
+                if (finish == GRRT_STOP_ERROR) atomicAdd(A.counters + CNT_ERRORS, 1ull);
+            }
             state = ST_IDLE;
         }
     }
 
-    // ---------------- counters: warp-reduce, one atomic per warp ----------------
-    if (A.counters) {
-        unsigned long long v[6] = {c_attempts, c_accepted, c_samples, c_errors, c_overflow, c_rays};
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            unsigned long long x = v[k];
-            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(kFull, x, off);
-            if (lane == 0 && x) atomicAdd(A.counters + k, x);
-        }
-    }
+#undef CTX
 }
-
 
 // ---- launch ---------------------------------------------------------------------------------------------
 template <int G, bool V, int MB>
