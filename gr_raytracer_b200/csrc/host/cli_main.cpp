@@ -1,0 +1,179 @@
+// cli_main.cpp -- `grrt`: the reference's command line (src/cli/cli.rs, src/main.rs:29-178) on top of libgrrt.
+//
+//   grrt [--width W --height H --step-size S --max-steps N --max-radius R --epsilon E --camera-position x,y,z
+//         --phi P --theta T --psi S --tone-mapping reinhard|global-linear --show-sampling-mask
+//         --sampling-mask-color R,G,B] --config-file scene.toml
+//        render [--filename render.png] [--from-row .. --from-col .. --to-row .. --to-col ..]
+//      | render-ray --row R --col C [--filename rendered-ray.csv]
+//      | render-ray-at --position x,y,z --direction x,y,z [--filename rendered-ray-at.csv]
+//
+// Extra (not in the reference): --resource-root DIR (prefix for relative texture paths), --device N.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/grrt.h"
+
+namespace {
+
+[[noreturn]] void die(const std::string& msg) {
+    std::fprintf(stderr, "Error: %s\n", msg.c_str());
+    std::exit(1);
+}
+std::vector<double> parse_list(const std::string& s, const char* what) {
+    std::vector<double> out;
+    size_t p = 0;
+    while (p <= s.size()) {
+        size_t q = s.find(',', p);
+        if (q == std::string::npos) q = s.size();
+        std::string tok = s.substr(p, q - p);
+        char* end = nullptr;
+        double v = std::strtod(tok.c_str(), &end);
+        if (tok.empty() || !end || *end != '\0') die(std::string("invalid value '") + s + "' for " + what);
+        out.push_back(v);
+        p = q + 1;
+    }
+    return out;
+}
+bool ends_with(const std::string& s, const char* suf) {
+    size_t n = std::strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    GrrtCliOpts opts;
+    grrt_cli_opts_default(&opts);
+    std::string config_file, action, filename, resource_root;
+    long long from_row = -1, from_col = -1, to_row = -1, to_col = -1, ray_row = -1, ray_col = -1;
+    std::vector<double> at_pos, at_dir;
+    int device = 0;
+
+    std::vector<std::string> args(argv + 1, argv + argc);
+    auto value = [&](size_t& i, const std::string& flag) -> std::string {
+        // --flag=value or --flag value
+        const std::string& a = args[i];
+        size_t eq = a.find('=');
+        if (eq != std::string::npos) return a.substr(eq + 1);
+        if (i + 1 >= args.size()) die("a value is required for '" + flag + "'");
+        return args[++i];
+    };
+    for (size_t i = 0; i < args.size(); ++i) {
+        std::string a = args[i];
+        std::string flag = a.substr(0, a.find('='));
+        if (flag == "--width") opts.width = std::atoll(value(i, flag).c_str());
+        else if (flag == "--height") opts.height = std::atoll(value(i, flag).c_str());
+        else if (flag == "--step-size") opts.step_size = std::atof(value(i, flag).c_str());
+        else if (flag == "--max-steps") opts.max_steps = std::strtoull(value(i, flag).c_str(), nullptr, 10);
+        else if (flag == "--max-radius") opts.max_radius = std::atof(value(i, flag).c_str());
+        else if (flag == "--epsilon") opts.epsilon = std::atof(value(i, flag).c_str());
+        else if (flag == "--camera-position") {
+            std::vector<double> v = parse_list(value(i, flag), "--camera-position");
+            if (v.size() != 3) die("Invalid configuration: Camera position must be a vector of length 3");
+            for (int k = 0; k < 3; ++k) opts.camera_position[k] = v[k];
+        } else if (flag == "--phi") opts.phi = std::atof(value(i, flag).c_str());
+        else if (flag == "--theta") opts.theta = std::atof(value(i, flag).c_str());
+        else if (flag == "--psi") opts.psi = std::atof(value(i, flag).c_str());
+        else if (flag == "--tone-mapping") {
+            std::string v = value(i, flag);
+            if (v == "reinhard") opts.tone_mapping = GRRT_TONEMAP_REINHARD;
+            else if (v == "global-linear") opts.tone_mapping = GRRT_TONEMAP_GLOBAL_LINEAR;
+            else die("invalid value '" + v + "' for '--tone-mapping' [possible values: reinhard, global-linear]");
+        } else if (flag == "--show-sampling-mask") opts.show_sampling_mask = 1;
+        else if (flag == "--sampling-mask-color") {
+            std::string raw = value(i, flag);
+            std::vector<double> v = parse_list(raw, "--sampling-mask-color");
+            if (v.size() != 3) die("invalid RGB color '" + raw + "'; expected R,G,B (for example 255,0,255)");
+            for (int k = 0; k < 3; ++k) {
+                if (v[k] < 0 || v[k] > 255 || v[k] != (double)(int)v[k]) die("invalid RGB color '" + raw + "'; expected three values from 0 to 255");
+                opts.sampling_mask_color[k] = (uint8_t)v[k];
+            }
+        } else if (flag == "--config-file" || flag == "-c") config_file = value(i, flag);
+        else if (flag == "--resource-root") resource_root = value(i, flag);
+        else if (flag == "--device") device = std::atoi(value(i, flag).c_str());
+        else if (flag == "--filename") filename = value(i, flag);
+        else if (flag == "--from-row") from_row = std::atoll(value(i, flag).c_str());
+        else if (flag == "--from-col") from_col = std::atoll(value(i, flag).c_str());
+        else if (flag == "--to-row") to_row = std::atoll(value(i, flag).c_str());
+        else if (flag == "--to-col") to_col = std::atoll(value(i, flag).c_str());
+        else if (flag == "--row" || flag == "-r") ray_row = std::atoll(value(i, flag).c_str());
+        else if (flag == "--col") ray_col = std::atoll(value(i, flag).c_str());
+        else if (flag == "--position" || flag == "-p") at_pos = parse_list(value(i, flag), "--position");
+        else if (flag == "--direction" || flag == "-d") at_dir = parse_list(value(i, flag), "--direction");
+        else if (a == "render" || a == "render-ray" || a == "render-ray-at") action = a;
+        else if (a == "blackbody" || a == "blackbody-spectrum") die("subcommand '" + a + "' is not part of the geodesic path and is not provided by grrt");
+        else die("unexpected argument '" + a + "'");
+    }
+    if (action.empty()) die("a subcommand is required: render | render-ray | render-ray-at");
+    if (config_file.empty()) die("Invalid configuration: Config file is required for this action");
+
+    auto t0 = std::chrono::steady_clock::now();
+    char err[1024] = {0};
+    GrrtHostScene* hs = nullptr;
+    int rc = grrt_host_scene_from_toml_file(config_file.c_str(), resource_root.empty() ? nullptr : resource_root.c_str(), &opts, &hs,
+                                            err, sizeof err);
+    if (rc) die(err);
+    const GrrtScene* scene = grrt_host_scene_get(hs);
+    GrrtCtx* ctx = nullptr;
+    if (grrt_init(device, &ctx) != 0) die("no usable CUDA device (sm_100): grrt has no CPU fallback");
+
+    if (action == "render") {
+        if (filename.empty()) filename = "render.png";
+        uint32_t fr = from_row < 0 ? 0 : (uint32_t)from_row, fc = from_col < 0 ? 0 : (uint32_t)from_col;
+        uint32_t tr = to_row < 0 ? (uint32_t)scene->camera.rows : (uint32_t)to_row;
+        uint32_t tc = to_col < 0 ? (uint32_t)scene->camera.cols : (uint32_t)to_col;
+        if (tr < fr || tc < fc) die("Invalid configuration: empty section");
+        size_t n = (size_t)(tr - fr) * (tc - fc);
+        std::vector<double> xyza(4 * n);
+        GrrtStats st;
+        rc = grrt_render(ctx, scene, fr, fc, tr, tc, xyza.data(), nullptr, nullptr, nullptr, &st);
+        if (rc) die(grrt_last_error(ctx));
+        if (ends_with(filename, ".hdr")) {  // raytracer.rs:468-480
+            if (grrt_host_write_hdr_xyz(filename.c_str(), xyza.data(), tc - fc, tr - fr)) die("I/O error: cannot write " + filename);
+        } else {
+            std::vector<uint8_t> rgb(3 * n);
+            rc = grrt_tonemap(ctx, xyza.data(), n, opts.tone_mapping, 1.0, rgb.data());
+            if (rc) die(grrt_last_error(ctx));
+            if (grrt_host_write_png_rgb8(filename.c_str(), rgb.data(), tc - fc, tr - fr)) die("I/O error: cannot write " + filename);
+        }
+        std::fprintf(stderr,
+                     "[grrt] %llu base rays + %llu sub-sample rays (%llu pixels supersampled), %llu RKF45 steps, %llu attempts, "
+                     "%llu ray-march samples, %llu ray errors; device %.1f ms\n",
+                     (unsigned long long)st.rays_base, (unsigned long long)st.rays_supersample, (unsigned long long)st.pixels_supersampled,
+                     (unsigned long long)st.accepted_steps, (unsigned long long)st.attempts, (unsigned long long)st.raymarch_samples,
+                     (unsigned long long)st.ray_errors, st.device_ms_total);
+        std::fprintf(stderr, "[grrt] saved image to %s\n", filename.c_str());
+    } else {
+        std::vector<GrrtStep> steps(scene->integration.max_steps ? scene->integration.max_steps : 1);
+        uint64_t n = 0;
+        int32_t stop = 0;
+        if (action == "render-ray") {
+            if (ray_row < 0 || ray_col < 0) die("render-ray needs --row and --col");
+            if (filename.empty()) filename = "rendered-ray.csv";
+            rc = grrt_trace_pixel_ray(ctx, scene, ray_row, ray_col, steps.data(), steps.size(), &n, &stop);
+        } else {
+            if (at_pos.size() != 3) die("Invalid configuration: Position must be a vector of length 3");
+            if (at_dir.size() != 3) die("Invalid configuration: Direction must be a vector of length 3");
+            if (filename.empty()) filename = "rendered-ray-at.csv";
+            double pos[4], mom[4];
+            if (grrt_host_ray_at(&scene->geometry, at_pos.data(), at_dir.data(), pos, mom, err, sizeof err)) die(err);
+            rc = grrt_trace_ray(ctx, scene, pos, mom, steps.data(), steps.size(), &n, &stop);
+        }
+        if (rc < 0) die(grrt_last_error(ctx));
+        if (rc > 0) die("Integration error: Max steps reached");  // IntegrationError::MaxStepsReached
+        if (n > steps.size()) n = steps.size();
+        if (grrt_host_write_ray_csv(&scene->geometry, steps.data(), n, filename.c_str())) die("I/O error: cannot write " + filename);
+        static const char* names[] = {"None", "HorizonReached", "CelestialSphereReached", "CoordinateIsNan", "ClosedOrbitDetected", "Error"};
+        std::fprintf(stderr, "[grrt] Stop reason: %s; saved integrated ray (%llu steps) to %s\n", names[stop < 0 || stop > 5 ? 5 : stop],
+                     (unsigned long long)n, filename.c_str());
+    }
+    grrt_destroy(ctx);
+    grrt_host_scene_free(hs);
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::fprintf(stderr, "[grrt] Elapsed time: %.2fs\n", secs);
+    return 0;
+}

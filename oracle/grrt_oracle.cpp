@@ -2447,3 +2447,49 @@ void orc_xyz_to_srgb(const double xyz[3], double exposure, uint8_t out[3]) {  //
 }
 
 }  // extern "C"
+
+// Same contract as grrt_trace_items_device (include/grrt.h), on the CPU: lets the multi-rank host logic of
+// gr_raytracer_b200/renderer.py be tested under gloo without a GPU (tests/test_distributed_cpu.py).
+extern "C" int orc_trace_items(const GrrtScene* s, const uint32_t* items, uint64_t first_item, uint64_t n_items,
+                               uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col, uint32_t spa,
+                               double* xyza, uint8_t* cls, uint8_t* stop, uint32_t* steps) {
+    SceneView sv = view_of(s);
+    (void)to_row;
+    const uint32_t W = to_col - from_col;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < (int64_t)n_items; ++i) {
+        uint64_t pid = items ? items[i] : first_item + (uint64_t)i;
+        int64_t row = (int64_t)(pid / W) + from_row, col = (int64_t)(pid % W) + from_col;
+        if (spa == 0) {
+            RayResult r = trace_ray(sv, camera_ray(s->camera, row, col), true, [](const StepRec&) {});
+            double* o = xyza + 4 * i;
+            if (r.error) {
+                o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 1.0;
+                if (cls) cls[i] = GRRT_CLASS_ESCAPED;
+            } else {
+                o[0] = r.color.x; o[1] = r.color.y; o[2] = r.color.z; o[3] = r.color.alpha;
+                if (cls) cls[i] = (uint8_t)r.ray_class;
+            }
+            if (stop) stop[i] = (uint8_t)r.stop;
+            if (steps) steps[i] = (uint32_t)r.steps;
+        } else {
+            Cie acc = cie(0.0, 0.0, 0.0, 0.0);
+            uint32_t valid = 0;
+            for (uint64_t sr = 0; sr < spa; ++sr)
+                for (uint64_t sc2 = 0; sc2 < spa; ++sc2) {
+                    double dx, dy;
+                    stratified_sample_offset(row, col, sr, sc2, spa, dx, dy);
+                    RayResult r = trace_ray(sv, camera_ray_offset(s->camera, row, col, dx, dy), true, [](const StepRec&) {});
+                    if (r.error) continue;
+                    acc = cie(acc.x + r.color.x, acc.y + r.color.y, acc.z + r.color.z, acc.alpha + r.color.alpha);
+                    ++valid;
+                }
+            if (valid > 0) {
+                double inv = 1.0 / (double)valid;
+                double* o = xyza + 4 * pid;
+                o[0] = acc.x * inv; o[1] = acc.y * inv; o[2] = acc.z * inv; o[3] = acc.alpha * inv;
+            }
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,66 @@
+"""The `grrt` command line (the reference's clap surface, src/cli/cli.rs) end to end on the GPU: render to PNG/HDR,
+render-ray / render-ray-at CSV export, error exits."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from gr_raytracer_b200 import abi, api
+from oracle import scene as osc
+from helpers import ROOT, CONFIGS, config_opts
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "gr_raytracer_b200", "grrt")
+
+
+def run(args, cwd):
+    return subprocess.run([EXE, "--resource-root", ROOT] + args, cwd=cwd, capture_output=True, text=True)
+
+
+def test_render_png_matches_oracle_tonemap(tmp_path):
+    from PIL import Image
+    args = ["--width", "40", "--height", "30", "--camera-position=-10,0,-0.5", "--theta=-3.14159",
+            "--config-file", os.path.join(ROOT, "scenes/kerr-bl.toml"), "render", "--filename", "out.png"]
+    r = run(args, tmp_path)
+    assert r.returncode == 0, r.stderr
+    img = np.array(Image.open(tmp_path / "out.png"))
+    assert img.shape == (30, 40, 3)
+    sc = osc.scene_from_toml(os.path.join(ROOT, "scenes/kerr-bl.toml"), config_opts("C2", width=40, height=30), ROOT)
+    ora = osc.render(sc)
+    ref = np.zeros((30 * 40, 3), dtype=np.uint8)
+    osc.lib().orc_tonemap(osc.dptr(np.ascontiguousarray(ora["xyza"].reshape(-1, 4))), 30 * 40, abi.TONEMAP_REINHARD, 1.0, osc.u8ptr(ref))
+    diff = np.abs(img.reshape(-1, 3).astype(int) - ref.astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.01
+    # section render + HDR output
+    r = run(args[:-2] + ["--filename", "crop.hdr", "--from-row", "5", "--to-row", "25", "--from-col", "10", "--to-col", "30"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "crop.hdr", "rb").read(10) == b"#?RADIANCE"
+
+
+def test_render_ray_csv_matches_oracle(tmp_path):
+    cfg = os.path.join(ROOT, "scenes/schwarzschild.toml")
+    r = run(["--max-steps", "10", "--config-file", cfg, "render-ray", "--row", "250", "--col", "250"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    lines = open(tmp_path / "rendered-ray.csv").read().split("\n")
+    assert lines[0] == "i,t,tau,x,y,z" and len(lines) == 12   # cli/schwarzschild.rs:133-172: header + 10 steps + trailing newline
+    sc = osc.scene_from_toml(cfg, abi.default_cli_opts(max_steps=10), ROOT)
+    steps, _, _ = osc.trace_ray(sc, pixel=(250, 250))
+    for k, line in enumerate(lines[1:11]):
+        f = [float(v) for v in line.split(",")]
+        cart = (osc.C.c_double * 4)()
+        osc.lib().orc_step_to_cartesian(osc.C.byref(sc.c.geometry), osc.darr(steps["x"][k]), cart)
+        assert int(f[0]) == k and f[1] == pytest.approx(steps["t"][k], rel=1e-12, abs=1e-15)
+        assert f[2:] == pytest.approx(list(cart), rel=1e-9, abs=1e-12)
+    r = run(["--max-steps", "50", "--config-file", os.path.join(ROOT, "scenes/kerr.toml"), "render-ray-at", "--position=-10,0,2",
+             "--direction=1,0,0", "--filename", "at.csv"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert len(open(tmp_path / "at.csv").read().split("\n")) == 52
+
+
+def test_cli_errors(tmp_path):
+    assert run(["render"], tmp_path).returncode != 0                                   # no config file
+    r = run(["--config-file", "missing.toml", "render"], tmp_path)
+    assert r.returncode != 0 and "Config file not found" in r.stderr                   # main.rs:67-73
+    r = run(["--camera-position=1,2", "--config-file", os.path.join(ROOT, "scenes/kerr.toml"), "render"], tmp_path)
+    assert r.returncode != 0 and "length 3" in r.stderr                                # main.rs:85-89
