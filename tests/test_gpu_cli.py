@@ -55,7 +55,16 @@ def test_render_ray_csv_matches_oracle(tmp_path):
     r = run(["--max-steps", "50", "--config-file", os.path.join(ROOT, "scenes/kerr.toml"), "render-ray-at", "--position=-10,0,2",
              "--direction=1,0,0", "--filename", "at.csv"], tmp_path)
     assert r.returncode == 0, r.stderr
-    assert len(open(tmp_path / "at.csv").read().split("\n")) == 52
+    # same ray through the oracle: momentum from the unboosted tetrad (cli/kerr.rs:77-100), then Integrator::integrate
+    import ctypes as C
+    sck = osc.scene_from_toml(os.path.join(ROOT, "scenes/kerr.toml"), abi.default_cli_opts(max_steps=50), ROOT)
+    pos, mom, err = (C.c_double * 4)(), (C.c_double * 4)(), C.create_string_buffer(256)
+    assert api.lib().grrt_host_ray_at(C.byref(sck.c.geometry), osc.darr([-10, 0, 2]), osc.darr([1, 0, 0]), pos, mom, err, 256) == 0
+    o_steps, _, _ = osc.trace_ray(sck, list(pos), list(mom))
+    at_lines = open(tmp_path / "at.csv").read().split("\n")
+    assert len(at_lines) == len(o_steps) + 2
+    last = [float(v) for v in at_lines[len(o_steps)].split(",")]
+    assert last[3:] == pytest.approx(list(o_steps["x"][-1][1:]), rel=1e-12)   # Kerr-Schild: bit-identical trajectory
 
 
 def test_cli_errors(tmp_path):
