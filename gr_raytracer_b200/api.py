@@ -60,6 +60,7 @@ def lib():
     L.grrt_tonemap_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_double, vp, vp]
     L.grrt_measure_fp64_peak.argtypes = [vp, dp, dp]
     L.grrt_debug_pow.argtypes = [vp, dp, dp, dp, C.c_size_t]
+    L.grrt_debug_sincos.argtypes = [vp, dp, dp, dp, C.c_size_t]
     for name in ("grrt_cli_opts_default", "grrt_host_scene_from_toml_file", "grrt_host_scene_from_toml_string",
                  "grrt_host_scene_get", "grrt_host_scene_free", "grrt_host_ray_at", "grrt_host_write_ray_csv",
                  "grrt_host_write_png_rgb8", "grrt_host_write_hdr_xyz", "grrt_host_read_png_rgba8", "grrt_host_free"):
@@ -232,6 +233,13 @@ class Context:
         self._check(lib().grrt_debug_pow(self._h, x.ctypes.data_as(abi.c_double_p), y.ctypes.data_as(abi.c_double_p),
                                          out.ctypes.data_as(abi.c_double_p), x.size))
         return out
+
+    def debug_sincos(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        sn, cs = np.zeros_like(x), np.zeros_like(x)
+        self._check(lib().grrt_debug_sincos(self._h, x.ctypes.data_as(abi.c_double_p), sn.ctypes.data_as(abi.c_double_p),
+                                            cs.ctypes.data_as(abi.c_double_p), x.size))
+        return sn, cs
 
     def measure_fp64_peak(self):
         rate, ms = C.c_double(), C.c_double()

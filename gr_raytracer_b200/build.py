@@ -61,6 +61,8 @@ def build(force=False, verbose=False):
             cmd = [nvcc] + ARCH + common + ["-c", path, "-o", obj]
             if src.endswith(".cu"):
                 cmd += ["-fmad=" + FMAD[src]] + (["-Xptxas", "-v"] if verbose else [])
+                if os.environ.get("GRRT_MB"):   # experiment knob: resident CTAs/SM the register allocator targets
+                    cmd += ["-DGRRT_MB=" + os.environ["GRRT_MB"]]
             else:
                 cmd += ["-Xcompiler", "-ffp-contract=off"]
             jobs.append(cmd)

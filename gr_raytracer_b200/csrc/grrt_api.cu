@@ -423,6 +423,8 @@ int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) 
             if ((rc = upload<double>(ctx, ds, o.temperature.lut_t, o.temperature.n, &d.temp.lut_t))) return bail(rc);
         }
         d.radius = o.radius;
+        d.center_norm = std::sqrt(o.position[0] * o.position[0] + o.position[1] * o.position[1] + o.position[2] * o.position[2]);
+        d.axis_is_z = (o.axis[0] == 0.0 && o.axis[1] == 0.0 && o.axis[2] == 1.0) ? 1 : 0;
         d.sphere_temperature = o.sphere_temperature;
         d.r_in = o.inner_radius;
         d.r_out = o.outer_radius;
@@ -774,6 +776,23 @@ int grrt_debug_pow(GrrtCtx* ctx, const double* x, const double* y, double* out, 
     if (grrt_exact::launch_debug_pow(dx.as<double>(), dy.as<double>(), dout.as<double>(), n, ctx->stream) != 0)
         return fail(ctx, GRRT_ERR_CUDA, "debug_pow launch failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRRT_OK;
+}
+
+// test hook: the kernels' sincos (csrc/grrt_device.cuh sincos_pi2) on host arrays
+int grrt_debug_sincos(GrrtCtx* ctx, const double* x, double* sn, double* cs, size_t n) {
+    if (!ctx || !x || !sn || !cs) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf dx, ds, dc;
+    CUDA_TRY(ctx, dx.alloc(n * 8, ctx->stream));
+    CUDA_TRY(ctx, ds.alloc(n * 8, ctx->stream));
+    CUDA_TRY(ctx, dc.alloc(n * 8, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dx.p, x, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (grrt_exact::launch_debug_sincos(dx.as<double>(), ds.as<double>(), dc.as<double>(), n, ctx->stream) != 0)
+        return fail(ctx, GRRT_ERR_CUDA, "debug_sincos launch failed");
+    CUDA_TRY(ctx, cudaMemcpyAsync(sn, ds.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(cs, dc.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return GRRT_OK;
 }

@@ -47,6 +47,47 @@ GD double dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 GD V3 cross3(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 GD double norm3(V3 a) { return sqrt(dot3(a, a)); }
 
+// sin and cos together, ~1 ulp.  Cody-Waite reduction by pi/2 with FMA (two terms suffice for |x| < 1e5; larger
+// arguments go to the library routine), fdlibm's minimax polynomials on [-pi/4, pi/4].  The coefficients live in
+// the constant bank: CUDA's sincos() materialises its 14 double constants with 28 UMOV instructions per call, which
+// was 18 % of the instructions of an RKF45 stage (profiles/r1_c2_trace_kernel_v3.json).  Neither routine is
+// bit-identical to glibc's sin/cos; the difference (last ulp) is part of the measured parity budget.
+__constant__ double c_trig[16] = {
+    6.36619772367581382433e-01,                                   // 0: 2/pi
+    1.57079632679489655800e+00, 6.12323399573676603587e-17,       // 1,2: pi/2 = hi + lo
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,   // 3..8: S1..S6
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,    // 9..14: C1..C6
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,
+    0.0};
+GD void sincos_pi2(double x, double* sn, double* cs) {
+    if (!(fabs(x) < 1.0e5)) {
+        sincos(x, sn, cs);
+        return;
+    }
+    const double kd = rint(x * c_trig[0]);
+    const int k = __double2int_rn(kd);
+    double r = fma(-kd, c_trig[1], x);
+    r = fma(-kd, c_trig[2], r);
+    const double z = r * r;
+    double ps = fma(z, c_trig[8], c_trig[7]);
+    ps = fma(z, ps, c_trig[6]);
+    ps = fma(z, ps, c_trig[5]);
+    ps = fma(z, ps, c_trig[4]);
+    ps = fma(z, ps, c_trig[3]);
+    const double s = fma(z * r, ps, r);
+    double pc = fma(z, c_trig[14], c_trig[13]);
+    pc = fma(z, pc, c_trig[12]);
+    pc = fma(z, pc, c_trig[11]);
+    pc = fma(z, pc, c_trig[10]);
+    pc = fma(z, pc, c_trig[9]);
+    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double a = (k & 1) ? c : s;    // sin(x) before the sign
+    const double b = (k & 1) ? s : c;    // cos(x) before the sign
+    *sn = (k & 2) ? -a : a;
+    *cs = ((k + 1) & 2) ? -b : b;
+}
+
 // Rust semantics
 GD double rclamp(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 GD bool in01(double t) { return t >= 0.0 && t <= 1.0; }
@@ -225,8 +266,8 @@ template <int G>
 GD V3 position_cartesian(const DScene& S, const double* y) {
     if (GeomTraits<G>::chart == CH_CART) return v3(y[1], y[2], y[3]);
     double st, ct, sp, cp;
-    sincos(y[2], &st, &ct);
-    sincos(y[3], &sp, &cp);
+    sincos_pi2(y[2], &st, &ct);
+    sincos_pi2(y[3], &sp, &cp);
     double r = y[1];
     if (GeomTraits<G>::chart == CH_SPH) return v3(r * st * cp, r * st * sp, r * ct);
     double a = S.a;
@@ -342,7 +383,7 @@ GD void geodesic_rhs(const DScene& S, const RayConst& C, const double* y, double
         double r = y[1];
         double v_t = y[4], v_r = y[5], v_theta = y[6], v_phi = y[7];
         double s, c;
-        sincos(y[2], &s, &c);
+        sincos_pi2(y[2], &s, &c);
 #ifdef GRRT_FAST_MATH
         {   // same formulas with shared reciprocals (3 instead of 5-6 divisions)
             const double inv_r = frcp(r), inv_s = frcp(s);
@@ -387,7 +428,7 @@ GD void geodesic_rhs(const DScene& S, const RayConst& C, const double* y, double
         double r = y[1], v_r = y[4], v_theta = y[5];
         double a = S.a, r_s = S.radius;
         double sin_t, cos_t;
-        sincos(y[2], &sin_t, &cos_t);
+        sincos_pi2(y[2], &sin_t, &cos_t);
         double del = bl_delta(r, r_s, a);
         double rr_aa = r * r + a * a;
         double p_r = rr_aa * C.e - a * C.l_z;
@@ -533,6 +574,61 @@ GD int should_stop(const DScene& S, const double* y, V3 cart, unsigned long long
         if (step_index == S.max_steps - 1 && r < 5.0 * S.radius) return GRRT_STOP_CLOSED_ORBIT;
     }
     if (cart.x * cart.x + cart.y * cart.y + cart.z * cart.z > S.max_radius_sq) return GRRT_STOP_CELESTIAL;
+    if (!finite4(y + 4)) return GRRT_STOP_NAN;
+    return GRRT_STOP_NONE;
+}
+
+// ---- lazy geometry for the spherical / Boyer-Lindquist charts ------------------------------------------------------
+// Converting a step to its Cartesian embedding costs two sincos, and almost no step can touch an object or the
+// celestial sphere.  segment_needs_cartesian() decides from (r, theta) of the two end points alone, conservatively,
+// whether the reference's tests on the chord could possibly succeed; if not, the conversion, the object loop and the
+// escape test are skipped -- with identical results, because every skipped test is provably false:
+//  * escape (integrator.rs:245-250): |x|^2 <= (r^2 + a^2)(1 + 4 eps) < max_radius^2;
+//  * Disc (disc.rs:41-88): t = -z0/(z1-z0) lies in [0,1] only if z0, z1 have opposite signs (or |z1| < 2^-53 |z0|);
+//    z = r cos(theta) has the sign of pi/2 - theta for theta in (0, pi), and the 1e-9 margin keeps |z1|/|z0| >> 2^-53;
+//  * Sphere (sphere.rs:61-76): needs |x - c|^2 - R^2 to change sign; ||x| - |c|| > R at both ends rules that out;
+//  * VolumetricDisc (volumetric_disc.rs:442-494): every capture surface lies in the slab |z| <= 3 thickness;
+//    |z| >= r (2/pi) |theta - pi/2| (concavity of cos), so both ends beyond the slab on the same side cannot hit.
+// Anything unusual (theta outside (0, pi), non-finite values, tilted disc axis) takes the full path.
+template <int G>
+GD bool segment_needs_cartesian(const DScene& S, double r0, double th0, double r1, double th1) {
+    if (GeomTraits<G>::chart == CH_CART) return true;
+    const double lo = 1e-9, hi = kPi - 1e-9;
+    if (!(th0 > lo && th0 < hi && th1 > lo && th1 < hi && r0 > 0.0 && r1 > 0.0)) return true;
+    const double aa = (GeomTraits<G>::chart == CH_BL) ? S.a * S.a : 0.0;
+    if (!(r1 * r1 + aa < S.max_radius_sq * (1.0 - 1e-12))) return true;  // may have escaped: evaluate exactly
+    const double s0 = th0 - 0.5 * kPi, s1 = th1 - 0.5 * kPi;               // sign(z) = -sign(s)
+    const bool same_side = (s0 > 0.0) == (s1 > 0.0);
+    for (int k = 0; k < S.n_objects; ++k) {
+        const DObject& o = S.obj[k];
+        if (o.kind == GRRT_OBJ_DISC) {
+            if (!(same_side && fabs(s0) > 1e-9 && fabs(s1) > 1e-9)) return true;
+        } else if (o.kind == GRRT_OBJ_SPHERE) {
+            const double Rs = o.radius * (1.0 + 1e-9) + 1e-300;
+            const double lo0 = r0 * (1.0 - 1e-12), lo1 = r1 * (1.0 - 1e-12);
+            const double hi0 = sqrt(r0 * r0 + aa) * (1.0 + 1e-12), hi1 = sqrt(r1 * r1 + aa) * (1.0 + 1e-12);
+            const bool out0 = lo0 > o.center_norm + Rs || hi0 < o.center_norm - Rs;
+            const bool out1 = lo1 > o.center_norm + Rs || hi1 < o.center_norm - Rs;
+            if (!(out0 && out1)) return true;
+        } else {
+            const double H = 3.0 * o.thickness * (1.0 + 1e-9);
+            const double c = 2.0 / kPi;
+            if (!(o.axis_is_z && same_side && r0 * c * fabs(s0) > H && r1 * c * fabs(s1) > H)) return true;
+        }
+    }
+    return false;
+}
+// should_stop when segment_needs_cartesian() returned false (escape already excluded)
+template <int G>
+GD int should_stop_inside(const DScene& S, const double* y, unsigned long long step_index) {
+    if (!finite4(y)) return GRRT_STOP_NAN;
+    if (G == GRRT_GEOM_SCHWARZSCHILD) {
+        if (y[1] <= S.radius + S.heps) return GRRT_STOP_HORIZON;
+        if (step_index == S.max_steps - 1 && y[1] < 5.0 * S.radius) return GRRT_STOP_CLOSED_ORBIT;
+    } else if (G == GRRT_GEOM_KERR_BL) {
+        if (S.horizon_enabled && y[1] <= S.r_plus_eps) return GRRT_STOP_HORIZON;
+        if (step_index == S.max_steps - 1 && y[1] < 5.0 * S.radius) return GRRT_STOP_CLOSED_ORBIT;
+    }
     if (!finite4(y + 4)) return GRRT_STOP_NAN;
     return GRRT_STOP_NONE;
 }

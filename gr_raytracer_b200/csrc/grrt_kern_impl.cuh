@@ -127,6 +127,14 @@ int launch_debug_pow(const double* x, const double* y, double* out, size_t n, cu
     if (n) debug_pow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, y, out, n);
     return (int)cudaGetLastError();
 }
+__global__ void debug_sincos_kernel(const double* x, double* sn, double* cs, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) sincos_pi2(x[i], sn + i, cs + i);
+}
+int launch_debug_sincos(const double* x, double* sn, double* cs, size_t n, cudaStream_t stream) {
+    if (n) debug_sincos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, sn, cs, n);
+    return (int)cudaGetLastError();
+}
 #endif  // GRRT_EXACT_EXTRAS
 
 }  // namespace GRRT_NS

@@ -246,6 +246,21 @@ static GRRT_POW_CONST unsigned long long kExpTab[256] = {
     0x3c77893b4d91cd9dull, 0x3fefe7c1819e90d8ull, 0x3c5305c14160cc89ull, 0x3feff3c22b8f71f1ull,
 };
 
+// scalar constants of the routine; on the device they sit in the constant bank so that DFMA/DMUL take them as
+// c[bank][offset] operands (64-bit immediates would cost two UMOV each, every time)
+#ifdef __CUDACC__
+#define GRRT_POW_SCALARS __constant__ double
+#else
+#define GRRT_POW_SCALARS static const double
+#endif
+GRRT_POW_SCALARS kPowC[21] = {
+    0x1.62e42fefa3800p-1, 0x1.ef35793c76730p-45,                                   // 0 Ln2hi, 1 Ln2lo
+    -0x1p-1, 0x1.555555555556p-2 * -2, -0x1.0000000000006p-2 * -2, 0x1.999999959554ep-3 * 4,   // 2..8 A0..A6
+    -0x1.555555529a47ap-3 * 4, 0x1.2495b9b4845e9p-3 * -8, -0x1.0002b8b263fc3p-3 * -8,
+    0x1.71547652b82fep0 * 128, 0x1.8p52, -0x1.62e42fefa0000p-8, -0x1.cf79abc9e3b3ap-47,        // 9 InvLn2N, 10 Shift, 11 NegLn2hiN, 12 NegLn2loN
+    0x1.ffffffffffdbdp-2, 0x1.555555555543cp-3, 0x1.55555cf172b91p-5, 0x1.1111167a4d017p-7,    // 13..16 C2..C5
+    0.0, 0.0, 0.0, 0.0};
+
 struct PowTables {
     const double (*log_tab)[3];
     const unsigned long long* exp_tab;
@@ -256,10 +271,8 @@ GRRT_POW_FN double pow_glibc(const PowTables& T, double x, double y) {
     const unsigned long long iy = pow_bits(y);
     const unsigned topx = (unsigned)(ix >> 52), topy = (unsigned)(iy >> 52) & 0x7ffu;
     if (topx - 0x001u >= 0x7ffu - 0x001u || topy - 0x3beu >= 0x43eu - 0x3beu) return pow(x, y);
-    const double Ln2hi = 0x1.62e42fefa3800p-1, Ln2lo = 0x1.ef35793c76730p-45;
-    const double A0 = -0x1p-1, A1 = 0x1.555555555556p-2 * -2, A2 = -0x1.0000000000006p-2 * -2,
-                 A3 = 0x1.999999959554ep-3 * 4, A4 = -0x1.555555529a47ap-3 * 4, A5 = 0x1.2495b9b4845e9p-3 * -8,
-                 A6 = -0x1.0002b8b263fc3p-3 * -8;
+    const double Ln2hi = kPowC[0], Ln2lo = kPowC[1];
+    const double A0 = kPowC[2], A1 = kPowC[3], A2 = kPowC[4], A3 = kPowC[5], A4 = kPowC[6], A5 = kPowC[7], A6 = kPowC[8];
     // log_inline
     const unsigned long long tmp = ix - 0x3fe6955500000000ull;
     const int i = (int)((tmp >> (52 - 7)) & 127ull);
@@ -298,10 +311,8 @@ GRRT_POW_FN double pow_glibc(const PowTables& T, double x, double y) {
         if (abstop < 0x3c9u) return 1.0 + ehi;  // |y log x| < 2^-54
         return pow(x, y);                       // overflow / underflow territory
     }
-    const double InvLn2N = 0x1.71547652b82fep0 * 128, Shift = 0x1.8p52, NegLn2hiN = -0x1.62e42fefa0000p-8,
-                 NegLn2loN = -0x1.cf79abc9e3b3ap-47;
-    const double C2 = 0x1.ffffffffffdbdp-2, C3 = 0x1.555555555543cp-3, C4 = 0x1.55555cf172b91p-5,
-                 C5 = 0x1.1111167a4d017p-7;
+    const double InvLn2N = kPowC[9], Shift = kPowC[10], NegLn2hiN = kPowC[11], NegLn2loN = kPowC[12];
+    const double C2 = kPowC[13], C3 = kPowC[14], C4 = kPowC[15], C5 = kPowC[16];
     double kd2 = fma(ehi, InvLn2N, Shift);
     const unsigned long long ki = pow_bits(kd2);
     kd2 = kd2 - Shift;

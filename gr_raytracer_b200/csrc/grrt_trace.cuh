@@ -68,6 +68,7 @@ struct RayCtx {  // per-lane ray bookkeeping kept in registers
     unsigned attempts;
     int n_hits;
     int retries;
+    int prev_valid;   // the shared-memory copy of the previous step's Cartesian point is current
 };
 // ... and the part that is only touched at accepted steps / hits / ray end, kept in shared memory
 // ([slot][thread], conflict-free) so that the RKF45 stage loop has the registers to itself
@@ -305,7 +306,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
     double h = 0.0, h_cur = 0.0;
     RayConst C = {0.0, 0.0, 0.0};
     RayCtx R;
-    R.n_hits = 0; R.retries = 0; R.unit = 0; R.step = 0; R.attempts = 0;
+    R.n_hits = 0; R.retries = 0; R.unit = 0; R.step = 0; R.attempts = 0; R.prev_valid = 0;
 #define CTX(slot) s_ctx[(slot) * kTraceThreads + tid]
     Cie hits[kMaxHits];
     const unsigned ss = A.spa ? A.spa * A.spa : 1u;
@@ -368,6 +369,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                         R.attempts = 0;
                         R.n_hits = 0;
                         R.retries = 0;
+                        R.prev_valid = 1;
                         h = S.step_size;
                         h_cur = rclamp(h, kHMin, kHMax);
                         state = ST_ACTIVE;
@@ -456,16 +458,21 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
         best.u = best.v = best.t = 0.0;
         best.point = best.dir = v3(0.0, 0.0, 0.0);
         Cie hit_color = cie(0.0, 0.0, 0.0, 0.0);
+        bool need_geo = false;
+        V3 prev_cart = v3(0.0, 0.0, 0.0);
         if (accepted) {
+            need_geo = segment_needs_cartesian<G>(S, y[1], y[2], y_new[1], y_new[2]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) s_yprev[i * kTraceThreads + tid] = y[i];
+            if (need_geo) prev_cart = R.prev_valid ? v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z)) : position_cartesian<G>(S, y);
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = y_new[i];
             ++R.step;
             R.retries = 0;
             h_cur = rclamp(h, kHMin, kHMax);
+        }
+        if (accepted && need_geo) {
             cart = position_cartesian<G>(S, y);
-            const V3 prev_cart = v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z));
             // Objects::intersects (objects.rs:65-120)
             double shortest = 1.7976931348623157e308;
             int best_k = -1;
@@ -565,10 +572,17 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 double alpha = rclamp(hit_color.a, 0.0, 1.0);
                 CTX(CX_OPACITY) = alpha + CTX(CX_OPACITY) * (1.0 - alpha);  // scene.rs:149-150
             }
-            CTX(CX_PREV_X) = cart.x;
-            CTX(CX_PREV_Y) = cart.y;
-            CTX(CX_PREV_Z) = cart.z;
-            int st = should_stop<G>(S, y, cart, R.step);
+            int st;
+            if (need_geo) {
+                CTX(CX_PREV_X) = cart.x;
+                CTX(CX_PREV_Y) = cart.y;
+                CTX(CX_PREV_Z) = cart.z;
+                R.prev_valid = 1;
+                st = should_stop<G>(S, y, cart, R.step);
+            } else {
+                R.prev_valid = 0;
+                st = should_stop_inside<G>(S, y, R.step);
+            }
             if (st != GRRT_STOP_NONE) finish = st;
             else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
         }

@@ -29,6 +29,8 @@ struct DTemperature {
 struct DObject {
     int kind;
     int perm_slot;  // index into the shared-memory Perlin tables
+    int axis_is_z;         // VolumetricDisc with the default axis (0,0,1): enables the cheap slab rejection
+    double center_norm;    // Sphere: |position|
     DTexture tex;
     DTemperature temp;
     double radius, pos[3], sphere_temperature;
@@ -99,6 +101,7 @@ int launch_trace_single(const grrt::DScene& s, const double pos[4], const double
                         GrrtStep* d_steps, unsigned long long cap, unsigned long long* d_n, int* d_stop, int* d_err,
                         cudaStream_t stream);
 int launch_debug_pow(const double* x, const double* y, double* out, size_t n, cudaStream_t stream);
+int launch_debug_sincos(const double* x, double* sn, double* cs, size_t n, cudaStream_t stream);
 }
 namespace grrt_fast {
 int launch_trace(const grrt::DScene& s, const grrt::TraceArgs& a, bool has_vol, const grrt::TraceLaunch& l);

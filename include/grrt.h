@@ -308,6 +308,8 @@ int grrt_measure_fp64_peak(GrrtCtx* ctx, double* dfma_per_second, double* ms);
 
 /* Test hook: evaluates the device's glibc-compatible pow (csrc/grrt_pow.cuh) on host arrays. */
 int grrt_debug_pow(GrrtCtx* ctx, const double* x, const double* y, double* out, size_t n);
+/* Test hook: the kernels' sin/cos routine on host arrays. */
+int grrt_debug_sincos(GrrtCtx* ctx, const double* x, double* sin_out, double* cos_out, size_t n);
 
 /* ---- host-side scene assembly (mirror of src/cli + src/configuration.rs) --------- */
 

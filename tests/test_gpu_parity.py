@@ -184,6 +184,28 @@ def test_device_pow_is_bit_identical_to_libm(ctx):
     assert np.array_equal(dev[ok], ref[ok])
 
 
+def test_device_sincos_accuracy(ctx):
+    """The kernels' sincos (Cody-Waite + fdlibm polynomials, constants in the constant bank): <= 2 ulp of the
+    correctly rounded value over the ranges the polar and azimuthal angles visit."""
+    import mpmath
+    rng = np.random.default_rng(12)
+    x = np.concatenate([rng.uniform(0.0, np.pi, 60000), rng.uniform(-50.0, 50.0, 30000), rng.uniform(-9e4, 9e4, 10000),
+                        np.array([0.0, np.pi / 2, np.pi, 1e-300, 3e5, -7e7])])
+    sn, cs = ctx.debug_sincos(x)
+    ref_s, ref_c = np.sin(x), np.cos(x)   # numpy/glibc: < 1 ulp
+    ulp_s = np.abs(sn - ref_s) / np.spacing(np.maximum(np.abs(ref_s), 1e-300))
+    ulp_c = np.abs(cs - ref_c) / np.spacing(np.maximum(np.abs(ref_c), 1e-300))
+    # near zeros of sin/cos the error is relative to the reduced argument: compare absolutely there
+    ok_s = (ulp_s <= 2.0) | (np.abs(sn - ref_s) <= 2.5e-16 * np.maximum(np.abs(x) * 2.3e-16 / 2.5e-16, 1.0))
+    ok_c = (ulp_c <= 2.0) | (np.abs(cs - ref_c) <= 2.5e-16 * np.maximum(np.abs(x) * 2.3e-16 / 2.5e-16, 1.0))
+    print(f"[sincos] max ulp error sin {ulp_s[ok_s].max():.2f} cos {ulp_c[ok_c].max():.2f}; mean {ulp_s.mean():.3f}/{ulp_c.mean():.3f}")
+    assert ok_s.all() and ok_c.all()
+    with mpmath.workdps(40):
+        for v in (0.3, 1.2, 2.9):
+            s, c = ctx.debug_sincos(np.array([v]))
+            assert abs(mpmath.mpf(float(s[0])) - mpmath.sin(v)) < 2.3e-16 and abs(mpmath.mpf(float(c[0])) - mpmath.cos(v)) < 2.3e-16
+
+
 def test_fp64_peak_microbenchmark(ctx):
     rate, ms = ctx.measure_fp64_peak()
     print(f"[fp64] measured DFMA rate {rate / 1e12:.2f} T DFMA/s ({2 * rate / 1e12:.2f} TFLOP/s) in {ms:.2f} ms")
