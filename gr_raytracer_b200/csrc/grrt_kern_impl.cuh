@@ -19,7 +19,7 @@ int launch_trace_v(const DScene& s, const TraceArgs& a, const TraceLaunch& l) {
         case GRRT_GEOM_SCHWARZSCHILD: return launch_trace_t<GRRT_GEOM_SCHWARZSCHILD, V, (V ? 3 : GRRT_MB)>(s, a, l);
         case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V, (V ? 3 : GRRT_MB)>(s, a, l);
 #ifdef GRRT_WITH_KERR_SCHILD
-        case GRRT_GEOM_KERR: return launch_trace_t<GRRT_GEOM_KERR, V, 2>(s, a, l);
+        case GRRT_GEOM_KERR: return launch_trace_t<GRRT_GEOM_KERR, V, (V ? 2 : 3)>(s, a, l);
 #endif
         default: return (int)cudaErrorInvalidValue;
     }
