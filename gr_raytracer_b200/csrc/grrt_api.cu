@@ -399,6 +399,7 @@ int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) 
     s.max_radius_sq = sc->integration.max_radius * sc->integration.max_radius;  // integrator.rs:62
     s.step_size = sc->integration.step_size;
     s.epsilon = sc->integration.epsilon;
+    s.inv_epsilon = 1.0 / sc->integration.epsilon;
     s.hit_opacity_threshold = sc->adaptive.object_hit_opacity_threshold;
     s.celestial_temperature = sc->celestial_temperature;
     s.srgb_lut = ctx->d_srgb_lut;

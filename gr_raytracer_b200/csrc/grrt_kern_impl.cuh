@@ -14,8 +14,8 @@ namespace GRRT_NS {
 template <bool V>
 int launch_trace_v(const DScene& s, const TraceArgs& a, const TraceLaunch& l) {
     switch (s.geom) {
-        case GRRT_GEOM_EUCLIDEAN: return launch_trace_t<GRRT_GEOM_EUCLIDEAN, V, 3>(s, a, l);
-        case GRRT_GEOM_EUCLIDEAN_SPHERICAL: return launch_trace_t<GRRT_GEOM_EUCLIDEAN_SPHERICAL, V, 3>(s, a, l);
+        case GRRT_GEOM_EUCLIDEAN: return launch_trace_t<GRRT_GEOM_EUCLIDEAN, V, (V ? 3 : 4)>(s, a, l);
+        case GRRT_GEOM_EUCLIDEAN_SPHERICAL: return launch_trace_t<GRRT_GEOM_EUCLIDEAN_SPHERICAL, V, (V ? 3 : 4)>(s, a, l);
         case GRRT_GEOM_SCHWARZSCHILD: return launch_trace_t<GRRT_GEOM_SCHWARZSCHILD, V, (V ? 3 : GRRT_MB)>(s, a, l);
         case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V, (V ? 3 : GRRT_MB)>(s, a, l);
 #ifdef GRRT_WITH_KERR_SCHILD

@@ -54,9 +54,19 @@ struct Comp {
     __host__ __device__ static constexpr bool on(int i) {
         return G == GRRT_GEOM_EUCLIDEAN ? i < 4 : (G == GRRT_GEOM_KERR_BL ? i < 6 : (G == GRRT_GEOM_KERR ? i != 4 : true));
     }
-    __host__ __device__ static constexpr int slot(int i) {  // dense index of an active component
+    // ... and which the right-hand side reads: only those need their stage derivatives k1..k5 kept, because the
+    // stage argument y + sum B k is dead for every other component (t and phi in the spherical charts, the
+    // positions in flat Cartesian space)
+    __host__ __device__ static constexpr bool read(int i) {
+        return G == GRRT_GEOM_EUCLIDEAN ? i >= 4
+             : G == GRRT_GEOM_KERR_BL  ? (i == 1 || i == 2 || i == 4 || i == 5)
+             : G == GRRT_GEOM_KERR     ? i != 0
+                                       : (i != 0 && i != 3);
+    }
+    __host__ __device__ static constexpr bool stored(int i) { return on(i) && read(i); }
+    __host__ __device__ static constexpr int slot(int i) {  // dense index of a stored component
         int n = 0;
-        for (int j = 0; j < i; ++j) n += on(j) ? 1 : 0;
+        for (int j = 0; j < i; ++j) n += stored(j) ? 1 : 0;
         return n;
     }
     static constexpr int count = slot(8);
@@ -434,17 +444,28 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 y_new[i] = y[i];
                 acc_e[i] = 0.0;
             }
+            double* const kcol = s_k + tid;  // this lane's column of the [stage][component][thread] k store
+            double* kst = kcol;
 #pragma unroll 1
             for (int s = 0; s < 6; ++s) {
                 double tmp[8];
+                if (s == 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) tmp[i] = y[i];
-#pragma unroll 1
-                for (int j = 0; j < s; ++j) {  // y + B_s1 k1 + B_s2 k2 + ... left to right
-                    const double b = c_rk_b[s][j];
+                    for (int i = 0; i < 8; ++i) tmp[i] = y[i];
+                } else {  // y + B_s1 k1 + B_s2 k2 + ... left to right
+                    const double* kj = kcol;
+                    const double b0 = c_rk_b[s][0];
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        if (Comp<G>::on(i)) tmp[i] = tmp[i] + b * s_k[(j * NC + Comp<G>::slot(i)) * kTraceThreads + tid];
+                        tmp[i] = Comp<G>::stored(i) ? y[i] + b0 * kj[Comp<G>::slot(i) * kTraceThreads] : y[i];
+#pragma unroll 1
+                    for (int j = 1; j < s; ++j) {
+                        kj += NC * kTraceThreads;
+                        const double b = c_rk_b[s][j];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (Comp<G>::stored(i)) tmp[i] = tmp[i] + b * kj[Comp<G>::slot(i) * kTraceThreads];
+                    }
                 }
                 double d[8];
                 geodesic_rhs<G>(S, C, tmp, d);
@@ -453,11 +474,12 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 for (int i = 0; i < 8; ++i) {
                     if (Comp<G>::on(i)) {
                         const double k = h_cur * d[i];
-                        if (s < 5) s_k[(s * NC + Comp<G>::slot(i)) * kTraceThreads + tid] = k;
+                        if (s < 5 && Comp<G>::stored(i)) kst[Comp<G>::slot(i) * kTraceThreads] = k;
                         y_new[i] = y_new[i] + ch * k;
                         acc_e[i] = acc_e[i] + ct * k;
                     }
                 }
+                kst += NC * kTraceThreads;
             }
             // truncation error: nalgebra's 8-accumulator dot product, (0,4) (1,5) (2,6) (3,7)
             double e[8];
@@ -470,6 +492,22 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
             const double err = sqrt(res);
             ++R.attempts;
             double h_proposed;
+#ifdef GRRT_FAST_MATH
+            // (epsilon/err)^(1/5) = q^(-1/5), q = err/epsilon: single-precision seed, then two steps of the
+            // division-free Newton iteration z <- z (1.2 - 0.2 q z^5) (error 3e^2 per step: 5e-6 -> 8e-11 -> < 1 ulp).
+            // Outside the seed's range (and for err = 0, inf, NaN) the exact path below decides.
+            const double q = err * S.inv_epsilon;
+            if (q > 1e-30 && q < 1e30) {
+                double z = (double)exp2f(-0.2f * __log2f((float)q));
+                const double mq = -0.2 * q;
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const double z2 = z * z;
+                    z = z * fma(mq, z2 * z2 * z, 1.2);
+                }
+                h_proposed = 0.9 * h_cur * z;
+            } else
+#endif
             if (err > 0.0) h_proposed = 0.9 * h_cur * pow_glibc(pow_tab, S.epsilon / err, 1.0 / 5.0);
             else h_proposed = h_cur * kHGrowthCap;
             h_proposed = rclamp(fmin(h_proposed, h_cur * kHGrowthCap), kHMin, kHMax);
@@ -486,85 +524,115 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 }
             } else {
                 accepted = true;
+#ifdef GRRT_FAST_MATH
+                h = (err * S.inv_epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
+#else
                 h = (err / S.epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
+#endif
             }
         }
-        // ---------------- accepted step: objects on the chord prev -> cur ----------------
-        V3 cart = v3(0.0, 0.0, 0.0);
-        bool have_hit = false;
+        // ---------------- accepted step: objects on the chord prev -> cur, stop tests ----------------
         int vol_k = -1;
-        Hit best;
-        best.u = best.v = best.t = 0.0;
-        best.point = best.dir = v3(0.0, 0.0, 0.0);
-        Cie hit_color = cie(0.0, 0.0, 0.0, 0.0);
-        bool need_geo = false;
-        V3 prev_cart = v3(0.0, 0.0, 0.0);
+        V3 vol_point = v3(0.0, 0.0, 0.0), vol_dir = v3(0.0, 0.0, 0.0);
+        int st = GRRT_STOP_NONE;
+        auto push_hit = [&](const Cie& hit_color) {
+            if (R.n_hits < kMaxHits) {
+                hits[R.n_hits++] = hit_color;
+            } else {  // fold into the last slot: "older over newer" keeps the compositing order
+                hits[kMaxHits - 1] = blend(hit_color, hits[kMaxHits - 1]);
+                if (A.counters) atomicAdd(A.counters + CNT_OVERFLOW, 1ull);
+            }
+            double alpha = rclamp(hit_color.a, 0.0, 1.0);
+            CTX(CX_OPACITY) = alpha + CTX(CX_OPACITY) * (1.0 - alpha);  // scene.rs:149-150
+        };
         if (accepted) {
-            need_geo = segment_needs_cartesian<G>(S, y[1], y[2], y_new[1], y_new[2]);
+            // far from every object and from the celestial sphere the chord needs no Cartesian end points and the
+            // previous state (only read when a hit is shaded) is not kept
+            const bool need_geo = segment_needs_cartesian<G>(S, y[1], y[2], y_new[1], y_new[2]);
+            V3 prev_cart = v3(0.0, 0.0, 0.0);
+            if (need_geo) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) s_yprev[i * kTraceThreads + tid] = y[i];
-            if (need_geo) prev_cart = R.prev_valid ? v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z)) : position_cartesian<G>(S, y);
+                for (int i = 0; i < 8; ++i) s_yprev[i * kTraceThreads + tid] = y[i];
+                prev_cart = R.prev_valid ? v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z)) : position_cartesian<G>(S, y);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = y_new[i];
             ++R.step;
             R.retries = 0;
             h_cur = rclamp(h, kHMin, kHMax);
-        }
-        if (accepted && need_geo) {
-            cart = position_cartesian<G>(S, y);
-            // Objects::intersects (objects.rs:65-120)
-            double shortest = 1.7976931348623157e308;
-            int best_k = -1;
-            double best_temperature = 0.0, best_redshift = 0.0;
-            for (int k = 0; k < S.n_objects; ++k) {
-                const DObject& o = S.obj[k];
-                Hit hcur;
-                bool hit;
-                if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
-                else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
-                else hit = vol_intersects(o, prev_cart, cart, hcur);
-                if (!hit) continue;
-                double distance = norm3(hcur.point - prev_cart);
-                if (!(distance < shortest)) continue;
-                shortest = distance;
-                // step_at_intersection (objects.rs:27-44): exact point, lerped momentum
-                double yp[8], p0[4], p1[4], xs[4], ps[4];
+            if (need_geo) {
+                const V3 cart = position_cartesian<G>(S, y);
+                // Objects::intersects (objects.rs:65-120)
+                double shortest = 1.7976931348623157e308;
+                int best_k = -1;
+                double best_temperature = 0.0, best_redshift = 0.0;
+                Hit best;
+                best.u = best.v = best.t = 0.0;
+                best.point = best.dir = v3(0.0, 0.0, 0.0);
+                for (int k = 0; k < S.n_objects; ++k) {
+                    const DObject& o = S.obj[k];
+                    Hit hcur;
+                    bool hit;
+                    if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
+                    else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
+                    else hit = vol_intersects(o, prev_cart, cart, hcur);
+                    if (!hit) continue;
+                    double distance = norm3(hcur.point - prev_cart);
+                    if (!(distance < shortest)) continue;
+                    shortest = distance;
+                    // step_at_intersection (objects.rs:27-44): exact point, lerped momentum
+                    double yp[8], p0[4], p1[4], xs[4], ps[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i * kTraceThreads + tid];
-                momentum_from_state<G>(S, C, yp, p0);
-                momentum_from_state<G>(S, C, y, p1);
-                double s = 1.0 - hcur.t;
+                    for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i * kTraceThreads + tid];
+                    momentum_from_state<G>(S, C, yp, p0);
+                    momentum_from_state<G>(S, C, y, p1);
+                    double s = 1.0 - hcur.t;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ps[i] = s * p0[i] + hcur.t * p1[i];
-                cartesian_to_native<G>(S, hcur.point, xs);
-                double vel[4];
-                if (o.kind == GRRT_OBJ_SPHERE) {
-                    stationary_velocity<G>(S, xs, vel);
-                } else if (!circular_orbit_velocity<G>(S, xs, vel)) {
-                    finish = GRRT_STOP_ERROR;
-                    ray_error = GRRT_RAYERR_NO_CIRCULAR_ORBIT;
-                    break;
-                }
-                double emitter_energy = inner_product<G>(S, xs, vel, ps);
-                best_redshift = (GeomTraits<G>::sig0 * CTX(CX_FREQ_E)) / (GeomTraits<G>::sig0 * emitter_energy);
-                if (o.kind == GRRT_OBJ_SPHERE) {
-                    best_temperature = o.sphere_temperature;
-                } else {
-                    int terr = compute_temperature(o.temp, radial_coordinate_cart<G>(S, hcur.point), best_temperature);
-                    if (terr) {
+                    for (int i = 0; i < 4; ++i) ps[i] = s * p0[i] + hcur.t * p1[i];
+                    cartesian_to_native<G>(S, hcur.point, xs);
+                    double vel[4];
+                    if (o.kind == GRRT_OBJ_SPHERE) {
+                        stationary_velocity<G>(S, xs, vel);
+                    } else if (!circular_orbit_velocity<G>(S, xs, vel)) {
                         finish = GRRT_STOP_ERROR;
-                        ray_error = terr;
+                        ray_error = GRRT_RAYERR_NO_CIRCULAR_ORBIT;
                         break;
                     }
+                    double emitter_energy = inner_product<G>(S, xs, vel, ps);
+                    best_redshift = (GeomTraits<G>::sig0 * CTX(CX_FREQ_E)) / (GeomTraits<G>::sig0 * emitter_energy);
+                    if (o.kind == GRRT_OBJ_SPHERE) {
+                        best_temperature = o.sphere_temperature;
+                    } else {
+                        int terr = compute_temperature(o.temp, radial_coordinate_cart<G>(S, hcur.point), best_temperature);
+                        if (terr) {
+                            finish = GRRT_STOP_ERROR;
+                            ray_error = terr;
+                            break;
+                        }
+                    }
+                    best = hcur;
+                    best_k = k;
                 }
-                best = hcur;
-                best_k = k;
-            }
-            if (finish != GRRT_STOP_ERROR && best_k >= 0) {
-                have_hit = true;
-                const DObject& o = S.obj[best_k];
-                if (o.kind == GRRT_OBJ_VOLUMETRIC_DISC) vol_k = best_k;
-                else hit_color = texture_color(S, o.tex, best.u, best.v, best_temperature, best_redshift);
+                if (finish != GRRT_STOP_ERROR) {
+                    if (best_k >= 0) {
+                        const DObject& o = S.obj[best_k];
+                        if (HAS_VOL && o.kind == GRRT_OBJ_VOLUMETRIC_DISC) {
+                            vol_k = best_k;  // shaded below by the whole warp
+                            vol_point = best.point;
+                            vol_dir = best.dir;
+                        } else {
+                            push_hit(texture_color(S, o.tex, best.u, best.v, best_temperature, best_redshift));
+                        }
+                    }
+                    CTX(CX_PREV_X) = cart.x;
+                    CTX(CX_PREV_Y) = cart.y;
+                    CTX(CX_PREV_Z) = cart.z;
+                    R.prev_valid = 1;
+                    st = should_stop<G>(S, y, cart, R.step);
+                }
+            } else {
+                R.prev_valid = 0;
+                st = should_stop_inside<G>(S, y, R.step);
             }
         }
 
@@ -576,13 +644,13 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 pending &= pending - 1;
                 const int k = __shfl_sync(kFull, vol_k, src);
                 V3 ro, rd;
-                ro.x = __shfl_sync(kFull, best.point.x, src);
-                ro.y = __shfl_sync(kFull, best.point.y, src);
-                ro.z = __shfl_sync(kFull, best.point.z, src);
+                ro.x = __shfl_sync(kFull, vol_point.x, src);
+                ro.y = __shfl_sync(kFull, vol_point.y, src);
+                ro.z = __shfl_sync(kFull, vol_point.z, src);
                 V3 dir;
-                dir.x = __shfl_sync(kFull, best.dir.x, src);
-                dir.y = __shfl_sync(kFull, best.dir.y, src);
-                dir.z = __shfl_sync(kFull, best.dir.z, src);
+                dir.x = __shfl_sync(kFull, vol_dir.x, src);
+                dir.y = __shfl_sync(kFull, vol_dir.y, src);
+                dir.z = __shfl_sync(kFull, vol_dir.z, src);
                 rd = dir / norm3(dir);  // .normalize() (volumetric_disc.rs:589-594)
                 const int src_tid = (tid & ~31) | src;
                 const double fe = s_ctx[CX_FREQ_E * kTraceThreads + src_tid];
@@ -593,35 +661,14 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 const DObject& o = S.obj[k];
                 Cie c = vol_march_warp<G>(S, o, s_perm + o.perm_slot * 256, ro, rd, fe, fpt, fpp, &merr, &smp);
                 if (lane == src) {
-                    hit_color = c;  // a failed march yields (0,0,0,0) (volumetric_disc.rs:596-600)
+                    push_hit(c);  // a failed march yields (0,0,0,0) (volumetric_disc.rs:596-600)
                     if (A.counters) atomicAdd(A.counters + CNT_SAMPLES, smp);
                 }
             }
         }
 
-        // ---------------- bookkeeping of the accepted step, stop tests, terminal colour ----------------
+        // ---------------- terminal event of the accepted step ----------------
         if (accepted && finish != GRRT_STOP_ERROR) {
-            if (have_hit) {
-                if (R.n_hits < kMaxHits) {
-                    hits[R.n_hits++] = hit_color;
-                } else {  // fold into the last slot: "older over newer" keeps the compositing order
-                    hits[kMaxHits - 1] = blend(hit_color, hits[kMaxHits - 1]);
-                    if (A.counters) atomicAdd(A.counters + CNT_OVERFLOW, 1ull);
-                }
-                double alpha = rclamp(hit_color.a, 0.0, 1.0);
-                CTX(CX_OPACITY) = alpha + CTX(CX_OPACITY) * (1.0 - alpha);  // scene.rs:149-150
-            }
-            int st;
-            if (need_geo) {
-                CTX(CX_PREV_X) = cart.x;
-                CTX(CX_PREV_Y) = cart.y;
-                CTX(CX_PREV_Z) = cart.z;
-                R.prev_valid = 1;
-                st = should_stop<G>(S, y, cart, R.step);
-            } else {
-                R.prev_valid = 0;
-                st = should_stop_inside<G>(S, y, R.step);
-            }
             if (st != GRRT_STOP_NONE) finish = st;
             else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
         }

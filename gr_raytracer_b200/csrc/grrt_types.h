@@ -55,6 +55,7 @@ struct DScene {
     // integration
     uint64_t max_steps;
     double max_radius_sq, step_size, epsilon;
+    double inv_epsilon;     // 1 / epsilon (fast build: error ratio without a division)
     double hit_opacity_threshold;
     DTexture celestial;
     double celestial_temperature;
