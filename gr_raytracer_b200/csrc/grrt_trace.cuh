@@ -72,6 +72,30 @@ struct Comp {
     static constexpr int count = slot(8);
 };
 
+// Fehlberg B coefficients as compile-time values (stage s = 1..5, term j < s)
+__host__ __device__ constexpr double rk_b(int s, int j) {
+    return s == 1 ? RK_B21
+         : s == 2 ? (j == 0 ? RK_B31 : RK_B32)
+         : s == 3 ? (j == 0 ? RK_B41 : j == 1 ? RK_B42 : RK_B43)
+         : s == 4 ? (j == 0 ? RK_B51 : j == 1 ? RK_B52 : j == 2 ? RK_B53 : RK_B54)
+                  : (j == 0 ? RK_B61 : j == 1 ? RK_B62 : j == 2 ? RK_B63 : j == 3 ? RK_B64 : RK_B65);
+}
+// argument of stage SS: y + B_s1 k1 + B_s2 k2 + ... summed left to right (runge_kutta.rs:95-124); straight-line so
+// that all shared-memory loads of a stage are issued together and the coefficients are instruction operands
+template <int G, int SS>
+__device__ __forceinline__ void stage_argument(const double* kcol, const double* y, double* tmp) {
+    constexpr int NC = Comp<G>::count;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double acc = y[i];
+        if (Comp<G>::stored(i)) {
+#pragma unroll
+            for (int j = 0; j < SS; ++j) acc = acc + rk_b(SS, j) * kcol[(j * NC + Comp<G>::slot(i)) * kTraceThreads];
+        }
+        tmp[i] = acc;
+    }
+}
+
 struct RayCtx {  // per-lane ray bookkeeping kept in registers
     unsigned long long unit;
     unsigned step;
@@ -449,23 +473,16 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
 #pragma unroll 1
             for (int s = 0; s < 6; ++s) {
                 double tmp[8];
-                if (s == 0) {
+                switch (s) {
+                    case 0:
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) tmp[i] = y[i];
-                } else {  // y + B_s1 k1 + B_s2 k2 + ... left to right
-                    const double* kj = kcol;
-                    const double b0 = c_rk_b[s][0];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        tmp[i] = Comp<G>::stored(i) ? y[i] + b0 * kj[Comp<G>::slot(i) * kTraceThreads] : y[i];
-#pragma unroll 1
-                    for (int j = 1; j < s; ++j) {
-                        kj += NC * kTraceThreads;
-                        const double b = c_rk_b[s][j];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (Comp<G>::stored(i)) tmp[i] = tmp[i] + b * kj[Comp<G>::slot(i) * kTraceThreads];
-                    }
+                        for (int i = 0; i < 8; ++i) tmp[i] = y[i];
+                        break;
+                    case 1: stage_argument<G, 1>(kcol, y, tmp); break;
+                    case 2: stage_argument<G, 2>(kcol, y, tmp); break;
+                    case 3: stage_argument<G, 3>(kcol, y, tmp); break;
+                    case 4: stage_argument<G, 4>(kcol, y, tmp); break;
+                    default: stage_argument<G, 5>(kcol, y, tmp); break;
                 }
                 double d[8];
                 geodesic_rhs<G>(S, C, tmp, d);
