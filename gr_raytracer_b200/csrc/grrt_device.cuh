@@ -610,11 +610,13 @@ GD bool segment_needs_cartesian(const DScene& S, double r0, double th0, double r
         if (o.kind == GRRT_OBJ_DISC) {
             if (!(same_side && fabs(s0) > 1e-9 && fabs(s1) > 1e-9)) return true;
         } else if (o.kind == GRRT_OBJ_SPHERE) {
+            // |x| lies in [r, sqrt(r^2 + a^2)]; compared as squares so that no square root is needed
             const double Rs = o.radius * (1.0 + 1e-9) + 1e-300;
-            const double lo0 = r0 * (1.0 - 1e-12), lo1 = r1 * (1.0 - 1e-12);
-            const double hi0 = sqrt(r0 * r0 + aa) * (1.0 + 1e-12), hi1 = sqrt(r1 * r1 + aa) * (1.0 + 1e-12);
-            const bool out0 = lo0 > o.center_norm + Rs || hi0 < o.center_norm - Rs;
-            const bool out1 = lo1 > o.center_norm + Rs || hi1 < o.center_norm - Rs;
+            const double far = o.center_norm + Rs, near = o.center_norm - Rs;
+            const double far2 = far * far * (1.0 + 1e-12), near2 = near * near * (1.0 - 1e-12);
+            const double q0 = r0 * r0, q1 = r1 * r1;
+            const bool out0 = q0 > far2 || (near > 0.0 && q0 + aa < near2);
+            const bool out1 = q1 > far2 || (near > 0.0 && q1 + aa < near2);
             if (!(out0 && out1)) return true;
         } else {
             const double H = 3.0 * o.thickness * (1.0 + 1e-9);

@@ -458,10 +458,24 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
         bool budget_empty = active && (S.max_steps <= 1);  // `for i in 1..max_steps` runs zero times
         if (budget_empty) finish = GRRT_STOP_NONE;
 
+        // per-step results that outlive the attempt block (the ray-march further down runs warp-converged)
+        int vol_k = -1;
+        V3 vol_point = v3(0.0, 0.0, 0.0), vol_dir = v3(0.0, 0.0, 0.0);
+        int st = GRRT_STOP_NONE;
+        auto push_hit = [&](const Cie& hit_color) {
+            if (R.n_hits < kMaxHits) {
+                hits[R.n_hits++] = hit_color;
+            } else {  // fold into the last slot: "older over newer" keeps the compositing order
+                hits[kMaxHits - 1] = blend(hit_color, hits[kMaxHits - 1]);
+                if (A.counters) atomicAdd(A.counters + CNT_OVERFLOW, 1ull);
+            }
+            double alpha = rclamp(hit_color.a, 0.0, 1.0);
+            CTX(CX_OPACITY) = alpha + CTX(CX_OPACITY) * (1.0 - alpha);  // scene.rs:149-150
+        };
         // ---------------- one RKF45 attempt (runge_kutta.rs:86-182, flattened retry loop) ----------------
-        double y_new[8];
-        bool accepted = false;
         if (active && !budget_empty) {
+            double y_new[8];
+            bool accepted = false;
             double acc_e[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -547,109 +561,100 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 h = (err / S.epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
 #endif
             }
-        }
-        // ---------------- accepted step: objects on the chord prev -> cur, stop tests ----------------
-        int vol_k = -1;
-        V3 vol_point = v3(0.0, 0.0, 0.0), vol_dir = v3(0.0, 0.0, 0.0);
-        int st = GRRT_STOP_NONE;
-        auto push_hit = [&](const Cie& hit_color) {
-            if (R.n_hits < kMaxHits) {
-                hits[R.n_hits++] = hit_color;
-            } else {  // fold into the last slot: "older over newer" keeps the compositing order
-                hits[kMaxHits - 1] = blend(hit_color, hits[kMaxHits - 1]);
-                if (A.counters) atomicAdd(A.counters + CNT_OVERFLOW, 1ull);
-            }
-            double alpha = rclamp(hit_color.a, 0.0, 1.0);
-            CTX(CX_OPACITY) = alpha + CTX(CX_OPACITY) * (1.0 - alpha);  // scene.rs:149-150
-        };
-        if (accepted) {
-            // far from every object and from the celestial sphere the chord needs no Cartesian end points and the
-            // previous state (only read when a hit is shaded) is not kept
-            const bool need_geo = segment_needs_cartesian<G>(S, y[1], y[2], y_new[1], y_new[2]);
-            V3 prev_cart = v3(0.0, 0.0, 0.0);
-            if (need_geo) {
+            // ---------------- accepted step: objects on the chord prev -> cur, stop tests ----------------
+            if (accepted) {
+                // far from every object and from the celestial sphere the chord needs no Cartesian end points and the
+                // previous state (only read when a hit is shaded) is not kept
+                const bool need_geo = segment_needs_cartesian<G>(S, y[1], y[2], y_new[1], y_new[2]);
+                V3 prev_cart = v3(0.0, 0.0, 0.0);
+                if (need_geo) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) s_yprev[i * kTraceThreads + tid] = y[i];
-                prev_cart = R.prev_valid ? v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z)) : position_cartesian<G>(S, y);
-            }
+                    for (int i = 0; i < 8; ++i) s_yprev[i * kTraceThreads + tid] = y[i];
+                    prev_cart = R.prev_valid ? v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z)) : position_cartesian<G>(S, y);
+                }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = y_new[i];
-            ++R.step;
-            R.retries = 0;
-            h_cur = rclamp(h, kHMin, kHMax);
-            if (need_geo) {
-                const V3 cart = position_cartesian<G>(S, y);
-                // Objects::intersects (objects.rs:65-120)
-                double shortest = 1.7976931348623157e308;
-                int best_k = -1;
-                double best_temperature = 0.0, best_redshift = 0.0;
-                Hit best;
-                best.u = best.v = best.t = 0.0;
-                best.point = best.dir = v3(0.0, 0.0, 0.0);
-                for (int k = 0; k < S.n_objects; ++k) {
-                    const DObject& o = S.obj[k];
-                    Hit hcur;
-                    bool hit;
-                    if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
-                    else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
-                    else hit = vol_intersects(o, prev_cart, cart, hcur);
-                    if (!hit) continue;
-                    double distance = norm3(hcur.point - prev_cart);
-                    if (!(distance < shortest)) continue;
-                    shortest = distance;
-                    // step_at_intersection (objects.rs:27-44): exact point, lerped momentum
-                    double yp[8], p0[4], p1[4], xs[4], ps[4];
+                for (int i = 0; i < 8; ++i) y[i] = y_new[i];
+                ++R.step;
+                R.retries = 0;
+                h_cur = rclamp(h, kHMin, kHMax);
+                if (need_geo) {
+                    const V3 cart = position_cartesian<G>(S, y);
+                    // Objects::intersects (objects.rs:65-120)
+                    double shortest = 1.7976931348623157e308;
+                    int best_k = -1;
+                    double best_temperature = 0.0, best_redshift = 0.0;
+                    Hit best;
+                    best.u = best.v = best.t = 0.0;
+                    best.point = best.dir = v3(0.0, 0.0, 0.0);
+                    for (int k = 0; k < S.n_objects; ++k) {
+                        const DObject& o = S.obj[k];
+                        Hit hcur;
+                        bool hit;
+                        if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
+                        else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
+                        else hit = vol_intersects(o, prev_cart, cart, hcur);
+                        if (!hit) continue;
+                        double distance = norm3(hcur.point - prev_cart);
+                        if (!(distance < shortest)) continue;
+                        shortest = distance;
+                        // step_at_intersection (objects.rs:27-44): exact point, lerped momentum
+                        double yp[8], p0[4], p1[4], xs[4], ps[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i * kTraceThreads + tid];
-                    momentum_from_state<G>(S, C, yp, p0);
-                    momentum_from_state<G>(S, C, y, p1);
-                    double s = 1.0 - hcur.t;
+                        for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i * kTraceThreads + tid];
+                        momentum_from_state<G>(S, C, yp, p0);
+                        momentum_from_state<G>(S, C, y, p1);
+                        double s = 1.0 - hcur.t;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) ps[i] = s * p0[i] + hcur.t * p1[i];
-                    cartesian_to_native<G>(S, hcur.point, xs);
-                    double vel[4];
-                    if (o.kind == GRRT_OBJ_SPHERE) {
-                        stationary_velocity<G>(S, xs, vel);
-                    } else if (!circular_orbit_velocity<G>(S, xs, vel)) {
-                        finish = GRRT_STOP_ERROR;
-                        ray_error = GRRT_RAYERR_NO_CIRCULAR_ORBIT;
-                        break;
-                    }
-                    double emitter_energy = inner_product<G>(S, xs, vel, ps);
-                    best_redshift = (GeomTraits<G>::sig0 * CTX(CX_FREQ_E)) / (GeomTraits<G>::sig0 * emitter_energy);
-                    if (o.kind == GRRT_OBJ_SPHERE) {
-                        best_temperature = o.sphere_temperature;
-                    } else {
-                        int terr = compute_temperature(o.temp, radial_coordinate_cart<G>(S, hcur.point), best_temperature);
-                        if (terr) {
+                        for (int i = 0; i < 4; ++i) ps[i] = s * p0[i] + hcur.t * p1[i];
+                        cartesian_to_native<G>(S, hcur.point, xs);
+                        double vel[4];
+                        if (o.kind == GRRT_OBJ_SPHERE) {
+                            stationary_velocity<G>(S, xs, vel);
+                        } else if (!circular_orbit_velocity<G>(S, xs, vel)) {
                             finish = GRRT_STOP_ERROR;
-                            ray_error = terr;
+                            ray_error = GRRT_RAYERR_NO_CIRCULAR_ORBIT;
                             break;
                         }
-                    }
-                    best = hcur;
-                    best_k = k;
-                }
-                if (finish != GRRT_STOP_ERROR) {
-                    if (best_k >= 0) {
-                        const DObject& o = S.obj[best_k];
-                        if (HAS_VOL && o.kind == GRRT_OBJ_VOLUMETRIC_DISC) {
-                            vol_k = best_k;  // shaded below by the whole warp
-                            vol_point = best.point;
-                            vol_dir = best.dir;
+                        double emitter_energy = inner_product<G>(S, xs, vel, ps);
+                        best_redshift = (GeomTraits<G>::sig0 * CTX(CX_FREQ_E)) / (GeomTraits<G>::sig0 * emitter_energy);
+                        if (o.kind == GRRT_OBJ_SPHERE) {
+                            best_temperature = o.sphere_temperature;
                         } else {
-                            push_hit(texture_color(S, o.tex, best.u, best.v, best_temperature, best_redshift));
+                            int terr = compute_temperature(o.temp, radial_coordinate_cart<G>(S, hcur.point), best_temperature);
+                            if (terr) {
+                                finish = GRRT_STOP_ERROR;
+                                ray_error = terr;
+                                break;
+                            }
                         }
+                        best = hcur;
+                        best_k = k;
                     }
-                    CTX(CX_PREV_X) = cart.x;
-                    CTX(CX_PREV_Y) = cart.y;
-                    CTX(CX_PREV_Z) = cart.z;
-                    R.prev_valid = 1;
-                    st = should_stop<G>(S, y, cart, R.step);
+                    if (finish != GRRT_STOP_ERROR) {
+                        if (best_k >= 0) {
+                            const DObject& o = S.obj[best_k];
+                            if (HAS_VOL && o.kind == GRRT_OBJ_VOLUMETRIC_DISC) {
+                                vol_k = best_k;  // shaded below by the whole warp
+                                vol_point = best.point;
+                                vol_dir = best.dir;
+                            } else {
+                                push_hit(texture_color(S, o.tex, best.u, best.v, best_temperature, best_redshift));
+                            }
+                        }
+                        CTX(CX_PREV_X) = cart.x;
+                        CTX(CX_PREV_Y) = cart.y;
+                        CTX(CX_PREV_Z) = cart.z;
+                        R.prev_valid = 1;
+                        st = should_stop<G>(S, y, cart, R.step);
+                    }
+                } else {
+                    R.prev_valid = 0;
+                    st = should_stop_inside<G>(S, y, R.step);
                 }
-            } else {
-                R.prev_valid = 0;
-                st = should_stop_inside<G>(S, y, R.step);
+                if (finish != GRRT_STOP_ERROR) {  // terminal event of the accepted step
+                    if (st != GRRT_STOP_NONE) finish = st;
+                    else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
+                }
             }
         }
 
@@ -682,12 +687,6 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                     if (A.counters) atomicAdd(A.counters + CNT_SAMPLES, smp);
                 }
             }
-        }
-
-        // ---------------- terminal event of the accepted step ----------------
-        if (accepted && finish != GRRT_STOP_ERROR) {
-            if (st != GRRT_STOP_NONE) finish = st;
-            else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
         }
 
         if (finish >= 0) {
