@@ -356,12 +356,17 @@ def main():
         roofline = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tflops,
                     "peak_source": "DFMA-chain microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); FMA = 2 flops",
                     "traffic": None}
+        if args.workload == "C2" and (W, H) == (1500, 1500) and world == 1:
+            # dram__bytes_read.sum + dram__bytes_write.sum of the base-pass launch, ncu --set full capture of this command
+            roofline["traffic"] = 23.763712e6 + 51.967232e6
+            roofline["traffic_source"] = "profiles/r1_c2_trace_kernel_v6_1500.json (bytes per base-pass launch; the frame buffers, no re-reads)"
         if kern_ms:
             ach = kern_flops / (kern_ms * 1e-3) / 1e12
             roofline.update({"achieved": ach, "frac": ach / peak_tflops, "kernel": "trace_kernel", "kernel_ms_per_launch": kern_ms,
                              "algorithmic_flops_per_launch": kern_flops,
-                             "note": "algorithmic FP64 ops of SURVEY.md 8(d) (divisions, sqrt and libm calls count 1 each); the kernel is "
-                                     "compiled without FMA contraction for bit-parity, so its issue-slot ceiling is half the FMA peak"})
+                             "note": "algorithmic FP64 ops of SURVEY.md 8(d) (divisions, sqrt and libm calls count 1 each) over the "
+                                     "mean trace_kernel launch time; Kerr-Schild scenes run the contraction-free build (bit parity), "
+                                     "whose issue-slot ceiling is half the FMA peak; the other geometries run the FMA build"})
         else:
             ach = flops / secs / 1e12
             roofline.update({"achieved": ach, "frac": ach / (peak_tflops * world), "kernel": "whole step, all ranks"})
