@@ -63,6 +63,8 @@ def build(force=False, verbose=False):
                 cmd += ["-fmad=" + FMAD[src]] + (["-Xptxas", "-v"] if verbose else [])
                 if os.environ.get("GRRT_MB"):   # experiment knob: resident CTAs/SM the register allocator targets
                     cmd += ["-DGRRT_MB=" + os.environ["GRRT_MB"]]
+                if os.environ.get("GRRT_MBV"):
+                    cmd += ["-DGRRT_MBV=" + os.environ["GRRT_MBV"]]
             else:
                 cmd += ["-Xcompiler", "-ffp-contract=off"]
             jobs.append(cmd)

@@ -988,21 +988,16 @@ GD unsigned perlin_hash(const uint8_t* perm, long long x, long long y, long long
     unsigned a = (unsigned)(x & 0xff), b = (unsigned)(y & 0xff), c = (unsigned)(z & 0xff);
     return perm[perm[perm[a] ^ b] ^ c];
 }
+// gradient dot product of noise 0.9.0 (core/perlin.rs: `match hash & 15`): one of (+-x +-y), (+-x +-z), (+-y +-z),
+// cases 12..15 repeating (x+y), (-x+y), (-y+z), (-y-z).  Branch-free -- a switch diverges 12 ways inside a warp --
+// with the same IEEE result: operands are selected, their sign bits flipped, then added once.
 GD double perlin_grad(unsigned hsh, double x, double y, double z) {
-    switch (hsh & 15u) {
-        case 0: case 12: return x + y;
-        case 1: case 13: return -x + y;
-        case 2: return x - y;
-        case 3: return -x - y;
-        case 4: return x + z;
-        case 5: return -x + z;
-        case 6: return x - z;
-        case 7: return -x - z;
-        case 8: return y + z;
-        case 9: case 14: return -y + z;
-        case 10: return y - z;
-        default: return -y - z;
-    }
+    const unsigned h = hsh & 15u;
+    const double u = ((0xCF00u >> h) & 1u) ? y : x;   // first operand is y for 8..11, 14, 15
+    const double v = ((0xCFF0u >> h) & 1u) ? z : y;   // second operand is z for 4..11, 14, 15
+    const unsigned long long su = (unsigned long long)((0xEAAAu >> h) & 1u) << 63;  // first operand negated
+    const unsigned long long sv = (unsigned long long)((0x8CCCu >> h) & 1u) << 63;  // second operand negated
+    return __longlong_as_double(__double_as_longlong(u) ^ (long long)su) + __longlong_as_double(__double_as_longlong(v) ^ (long long)sv);
 }
 GD double quintic(double x) { return x * x * x * (x * (x * 6.0 - 15.0) + 10.0); }
 GD double perlin_3d(const uint8_t* perm, double px, double py, double pz) {

@@ -11,13 +11,16 @@
 
 namespace GRRT_NS {
 
+#ifndef GRRT_MBV
+#define GRRT_MBV 3  // resident CTAs/SM the volumetric kernels are register-allocated for
+#endif
 template <bool V>
 int launch_trace_v(const DScene& s, const TraceArgs& a, const TraceLaunch& l) {
     switch (s.geom) {
-        case GRRT_GEOM_EUCLIDEAN: return launch_trace_t<GRRT_GEOM_EUCLIDEAN, V, (V ? 3 : 4)>(s, a, l);
-        case GRRT_GEOM_EUCLIDEAN_SPHERICAL: return launch_trace_t<GRRT_GEOM_EUCLIDEAN_SPHERICAL, V, (V ? 3 : 4)>(s, a, l);
-        case GRRT_GEOM_SCHWARZSCHILD: return launch_trace_t<GRRT_GEOM_SCHWARZSCHILD, V, (V ? 3 : GRRT_MB)>(s, a, l);
-        case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V, (V ? 3 : GRRT_MB)>(s, a, l);
+        case GRRT_GEOM_EUCLIDEAN: return launch_trace_t<GRRT_GEOM_EUCLIDEAN, V, (V ? GRRT_MBV : 4)>(s, a, l);
+        case GRRT_GEOM_EUCLIDEAN_SPHERICAL: return launch_trace_t<GRRT_GEOM_EUCLIDEAN_SPHERICAL, V, (V ? GRRT_MBV : 4)>(s, a, l);
+        case GRRT_GEOM_SCHWARZSCHILD: return launch_trace_t<GRRT_GEOM_SCHWARZSCHILD, V, (V ? GRRT_MBV : GRRT_MB)>(s, a, l);
+        case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V, (V ? GRRT_MBV : GRRT_MB)>(s, a, l);
 #ifdef GRRT_WITH_KERR_SCHILD
         case GRRT_GEOM_KERR: return launch_trace_t<GRRT_GEOM_KERR, V, (V ? 2 : 3)>(s, a, l);
 #endif

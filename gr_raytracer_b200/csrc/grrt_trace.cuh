@@ -106,7 +106,9 @@ struct RayCtx {  // per-lane ray bookkeeping kept in registers
 };
 // ... and the part that is only touched at accepted steps / hits / ray end, kept in shared memory
 // ([slot][thread], conflict-free) so that the RKF45 stage loop has the registers to itself
-enum { CX_FREQ_E = 0, CX_FREQ_PT = 1, CX_FREQ_PPHI = 2, CX_OPACITY = 3, CX_PREV_X = 4, CX_PREV_Y = 5, CX_PREV_Z = 6, CX_SLOTS = 7 };
+enum { CX_FREQ_E = 0, CX_FREQ_PT = 1, CX_FREQ_PPHI = 2, CX_OPACITY = 3, CX_PREV_X = 4, CX_PREV_Y = 5, CX_PREV_Z = 6, CX_SLOTS = 7,
+       // volumetric kernels only: hit point and chord direction handed to the warp-cooperative ray-march
+       CX_VOL_PX = 7, CX_VOL_PY = 8, CX_VOL_PZ = 9, CX_VOL_DX = 10, CX_VOL_DY = 11, CX_VOL_DZ = 12, CX_SLOTS_VOL = 13 };
 struct Freq {
     double e, pt, pphi;
 };
@@ -186,7 +188,7 @@ GD void init_ray(const DScene& S, const double pos[4], const double mom[4], doub
 // Every argument is warp-uniform.  Returns the march colour; *err receives a GRRT_RAYERR_* when
 // compute_temperature failed (the caller turns that into (0,0,0,0) as color_at_uv does, :596-600).
 template <int G>
-__device__ __noinline__ Cie vol_march_warp(const DScene& S, const DObject& o, const uint8_t* perm, V3 ro, V3 rd,
+__device__ __forceinline__ Cie vol_march_warp(const DScene& S, const DObject& o, const uint8_t* perm, V3 ro, V3 rd,
                                            double e_obs, double p_t, double p_phi, int* err,
                                            unsigned long long* samples) {
     const int lane = threadIdx.x & 31;
@@ -341,9 +343,16 @@ __device__ __noinline__ Cie vol_march_warp(const DScene& S, const DObject& o, co
 // ---- the kernel ----------------------------------------------------------------------------------------
 enum { ST_IDLE = 0, ST_ACTIVE = 1, ST_DEAD = 2 };
 
+// the exact build keeps the glibc-compatible pow tables in shared memory (one pow per attempt); the fast build only
+// needs them on the controller's rare fallback path and reads them from global memory
+#ifdef GRRT_FAST_MATH
+constexpr size_t kPowSmemBytes = 0;
+#else
+constexpr size_t kPowSmemBytes = sizeof(double) * 128 * 3 + 8 * 256;
+#endif
 template <int G, bool HAS_VOL>
 constexpr size_t trace_smem_bytes() {
-    return sizeof(double) * (size_t)(5 * Comp<G>::count + 8 + CX_SLOTS) * kTraceThreads + sizeof(double) * 128 * 3 + 8 * 256 +
+    return sizeof(double) * (size_t)(5 * Comp<G>::count + 8 + (HAS_VOL ? CX_SLOTS_VOL : CX_SLOTS)) * kTraceThreads + kPowSmemBytes +
            (HAS_VOL ? GRRT_MAX_OBJECTS * 256 : 0);
 }
 
@@ -355,16 +364,21 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
     double* s_k = reinterpret_cast<double*>(smem_raw);                       // [5][NC][threads]
     double* s_yprev = s_k + 5 * NC * kTraceThreads;                          // [8][threads]
     double* s_ctx = s_yprev + 8 * kTraceThreads;                             // [CX_SLOTS][threads]
-    double (*s_pow_log)[3] = reinterpret_cast<double (*)[3]>(s_ctx + CX_SLOTS * kTraceThreads);  // glibc-compatible pow tables
-    unsigned long long* s_pow_exp = reinterpret_cast<unsigned long long*>(s_pow_log + 128);
-    uint8_t* s_perm = reinterpret_cast<uint8_t*>(s_pow_exp + 256);           // [n_vol][256]
+    unsigned char* s_tail = reinterpret_cast<unsigned char*>(s_ctx + (HAS_VOL ? CX_SLOTS_VOL : CX_SLOTS) * kTraceThreads);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    PowTables pow_tab;
+#ifdef GRRT_FAST_MATH
+    pow_tab = pow_tables_global();
+#else
+    double (*s_pow_log)[3] = reinterpret_cast<double (*)[3]>(s_tail);        // glibc-compatible pow tables
+    unsigned long long* s_pow_exp = reinterpret_cast<unsigned long long*>(s_pow_log + 128);
     for (int i = tid; i < 128 * 3; i += kTraceThreads) (&s_pow_log[0][0])[i] = (&kPowLogTab[0][0])[i];
     for (int i = tid; i < 256; i += kTraceThreads) s_pow_exp[i] = kExpTab[i];
-    PowTables pow_tab;
     pow_tab.log_tab = s_pow_log;
     pow_tab.exp_tab = s_pow_exp;
+#endif
+    uint8_t* s_perm = reinterpret_cast<uint8_t*>(s_tail + kPowSmemBytes);    // [n_vol][256]
     if (HAS_VOL) {
         for (int k = 0; k < S.n_objects; ++k)
             if (S.obj[k].kind == GRRT_OBJ_VOLUMETRIC_DISC)
@@ -460,7 +474,6 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
 
         // per-step results that outlive the attempt block (the ray-march further down runs warp-converged)
         int vol_k = -1;
-        V3 vol_point = v3(0.0, 0.0, 0.0), vol_dir = v3(0.0, 0.0, 0.0);
         int st = GRRT_STOP_NONE;
         auto push_hit = [&](const Cie& hit_color) {
             if (R.n_hits < kMaxHits) {
@@ -635,8 +648,12 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                             const DObject& o = S.obj[best_k];
                             if (HAS_VOL && o.kind == GRRT_OBJ_VOLUMETRIC_DISC) {
                                 vol_k = best_k;  // shaded below by the whole warp
-                                vol_point = best.point;
-                                vol_dir = best.dir;
+                                CTX(CX_VOL_PX) = best.point.x;
+                                CTX(CX_VOL_PY) = best.point.y;
+                                CTX(CX_VOL_PZ) = best.point.z;
+                                CTX(CX_VOL_DX) = best.dir.x;
+                                CTX(CX_VOL_DY) = best.dir.y;
+                                CTX(CX_VOL_DZ) = best.dir.z;
                             } else {
                                 push_hit(texture_color(S, o.tex, best.u, best.v, best_temperature, best_redshift));
                             }
@@ -660,21 +677,21 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
 
         // ---------------- warp-cooperative ray-marches for lanes with a VolumetricDisc hit ----------------
         if (HAS_VOL) {
+            __syncwarp();  // the hit lanes' shared-memory hand-off is visible to the whole warp
             unsigned pending = __ballot_sync(kFull, vol_k >= 0);
             while (pending) {
                 const int src = __ffs(pending) - 1;
                 pending &= pending - 1;
                 const int k = __shfl_sync(kFull, vol_k, src);
-                V3 ro, rd;
-                ro.x = __shfl_sync(kFull, vol_point.x, src);
-                ro.y = __shfl_sync(kFull, vol_point.y, src);
-                ro.z = __shfl_sync(kFull, vol_point.z, src);
-                V3 dir;
-                dir.x = __shfl_sync(kFull, vol_dir.x, src);
-                dir.y = __shfl_sync(kFull, vol_dir.y, src);
-                dir.z = __shfl_sync(kFull, vol_dir.z, src);
-                rd = dir / norm3(dir);  // .normalize() (volumetric_disc.rs:589-594)
                 const int src_tid = (tid & ~31) | src;
+                V3 ro, rd, dir;
+                ro.x = s_ctx[CX_VOL_PX * kTraceThreads + src_tid];
+                ro.y = s_ctx[CX_VOL_PY * kTraceThreads + src_tid];
+                ro.z = s_ctx[CX_VOL_PZ * kTraceThreads + src_tid];
+                dir.x = s_ctx[CX_VOL_DX * kTraceThreads + src_tid];
+                dir.y = s_ctx[CX_VOL_DY * kTraceThreads + src_tid];
+                dir.z = s_ctx[CX_VOL_DZ * kTraceThreads + src_tid];
+                rd = dir / norm3(dir);  // .normalize() (volumetric_disc.rs:589-594)
                 const double fe = s_ctx[CX_FREQ_E * kTraceThreads + src_tid];
                 const double fpt = s_ctx[CX_FREQ_PT * kTraceThreads + src_tid];
                 const double fpp = s_ctx[CX_FREQ_PPHI * kTraceThreads + src_tid];
