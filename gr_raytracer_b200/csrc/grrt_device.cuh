@@ -91,7 +91,12 @@ GD void sincos_pi2(double x, double* sn, double* cs) {
 // Rust semantics
 GD double rclamp(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 GD bool in01(double t) { return t >= 0.0 && t <= 1.0; }
-GD bool finite4(const double* v) { return isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]) && isfinite(v[3]); }
+// all four finite; one exponent test on the OR-free form: a value is finite iff |v| <= DBL_MAX (false for NaN).
+// Evaluated without short-circuit branches -- the stop tests run once per accepted step.
+GD bool finite4(const double* v) {
+    const double m = 1.7976931348623157e308;
+    return (fabs(v[0]) <= m) & (fabs(v[1]) <= m) & (fabs(v[2]) <= m) & (fabs(v[3]) <= m);
+}
 GD double rem_euclid(double a, double b) {
     double r = fmod(a, b);
     return r < 0.0 ? r + fabs(b) : r;
@@ -565,23 +570,39 @@ GD void momentum_from_state(const DScene& S, const RayConst& C, const double* y,
 }
 
 // Integrator::should_stop position tests (integrator.rs:203-268); `cart` is the Cartesian embedding of y
+// The tests are evaluated branch-free and the first one that holds, in the reference's order, decides.
+template <int G>
+GD int stop_code(bool nan_pos, bool horizon, bool closed, bool escaped, bool nan_mom) {
+    int st = nan_mom ? GRRT_STOP_NAN : GRRT_STOP_NONE;
+    st = escaped ? GRRT_STOP_CELESTIAL : st;
+    st = closed ? GRRT_STOP_CLOSED_ORBIT : st;
+    st = horizon ? GRRT_STOP_HORIZON : st;
+    st = nan_pos ? GRRT_STOP_NAN : st;
+    return st;
+}
+template <int G>
+GD void horizon_tests(const DScene& S, const double* y, unsigned long long step_index, bool& horizon, bool& closed) {
+    horizon = false;
+    closed = false;
+    const bool last = step_index == S.max_steps - 1;
+    if (G == GRRT_GEOM_SCHWARZSCHILD) {
+        horizon = y[1] <= S.radius + S.heps;
+        closed = last & (y[1] < 5.0 * S.radius);
+    } else if (G == GRRT_GEOM_KERR_BL) {
+        horizon = (S.horizon_enabled != 0) & (y[1] <= S.r_plus_eps);
+        closed = last & (y[1] < 5.0 * S.radius);
+    } else if (G == GRRT_GEOM_KERR) {
+        const double r = sqrt(ks_r_sqr(S.a, y[1], y[2], y[3]));
+        horizon = (S.horizon_enabled != 0) & (r <= S.r_plus_eps);
+        closed = last & (r < 5.0 * S.radius);
+    }
+}
 template <int G>
 GD int should_stop(const DScene& S, const double* y, V3 cart, unsigned long long step_index) {
-    if (!finite4(y)) return GRRT_STOP_NAN;
-    if (G == GRRT_GEOM_SCHWARZSCHILD) {
-        if (y[1] <= S.radius + S.heps) return GRRT_STOP_HORIZON;
-        if (step_index == S.max_steps - 1 && y[1] < 5.0 * S.radius) return GRRT_STOP_CLOSED_ORBIT;
-    } else if (G == GRRT_GEOM_KERR_BL) {
-        if (S.horizon_enabled && y[1] <= S.r_plus_eps) return GRRT_STOP_HORIZON;
-        if (step_index == S.max_steps - 1 && y[1] < 5.0 * S.radius) return GRRT_STOP_CLOSED_ORBIT;
-    } else if (G == GRRT_GEOM_KERR) {
-        double r = sqrt(ks_r_sqr(S.a, y[1], y[2], y[3]));
-        if (S.horizon_enabled && r <= S.r_plus_eps) return GRRT_STOP_HORIZON;
-        if (step_index == S.max_steps - 1 && r < 5.0 * S.radius) return GRRT_STOP_CLOSED_ORBIT;
-    }
-    if (cart.x * cart.x + cart.y * cart.y + cart.z * cart.z > S.max_radius_sq) return GRRT_STOP_CELESTIAL;
-    if (!finite4(y + 4)) return GRRT_STOP_NAN;
-    return GRRT_STOP_NONE;
+    bool horizon, closed;
+    horizon_tests<G>(S, y, step_index, horizon, closed);
+    const bool escaped = cart.x * cart.x + cart.y * cart.y + cart.z * cart.z > S.max_radius_sq;
+    return stop_code<G>(!finite4(y), horizon, closed, escaped, !finite4(y + 4));
 }
 
 // ---- lazy geometry for the spherical / Boyer-Lindquist charts ------------------------------------------------------
@@ -629,16 +650,9 @@ GD bool segment_needs_cartesian(const DScene& S, double r0, double th0, double r
 // should_stop when segment_needs_cartesian() returned false (escape already excluded)
 template <int G>
 GD int should_stop_inside(const DScene& S, const double* y, unsigned long long step_index) {
-    if (!finite4(y)) return GRRT_STOP_NAN;
-    if (G == GRRT_GEOM_SCHWARZSCHILD) {
-        if (y[1] <= S.radius + S.heps) return GRRT_STOP_HORIZON;
-        if (step_index == S.max_steps - 1 && y[1] < 5.0 * S.radius) return GRRT_STOP_CLOSED_ORBIT;
-    } else if (G == GRRT_GEOM_KERR_BL) {
-        if (S.horizon_enabled && y[1] <= S.r_plus_eps) return GRRT_STOP_HORIZON;
-        if (step_index == S.max_steps - 1 && y[1] < 5.0 * S.radius) return GRRT_STOP_CLOSED_ORBIT;
-    }
-    if (!finite4(y + 4)) return GRRT_STOP_NAN;
-    return GRRT_STOP_NONE;
+    bool horizon, closed;
+    horizon_tests<G>(S, y, step_index, horizon, closed);
+    return stop_code<G>(!finite4(y), horizon, closed, false, !finite4(y + 4));
 }
 
 // ---- RKF45 tableau (runge_kutta.rs:16-84) ----------------------------------------------------------

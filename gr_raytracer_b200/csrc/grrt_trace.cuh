@@ -467,14 +467,158 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
         if (__ballot_sync(kFull, state != ST_DEAD) == 0) break;
 
         const bool active = state == ST_ACTIVE;
-        int finish = -1;       // >= 0: GRRT_STOP_* with which this lane's ray ends on this trip
+        int finish = -1;       // >= 0: GRRT_STOP_* with which this lane's ray ends
         int ray_error = 0;
-        bool budget_empty = active && (S.max_steps <= 1);  // `for i in 1..max_steps` runs zero times
-        if (budget_empty) finish = GRRT_STOP_NONE;
+        unsigned cand = 0;     // objects that were the nearest hit so far at their turn in Objects::intersects
+        if (active && S.max_steps <= 1) finish = GRRT_STOP_NONE;  // `for i in 1..max_steps` runs zero times
+        bool event = state == ST_IDLE || finish >= 0;
 
-        // per-step results that outlive the attempt block (the ray-march further down runs warp-converged)
-        int vol_k = -1;
-        int st = GRRT_STOP_NONE;
+        // ================= hot loop: RKF45 attempts until some lane of the warp has an event =================
+        // An event is a chord that hit an object (to be shaded), the end of a ray, or an idle lane.  Everything
+        // that handles events -- shading, the ray-march, terminal colour, write-out, fetching and launching the next
+        // ray -- sits outside this loop, so the loop body is one contiguous piece of code of ~1.5k instructions.
+        while (!__any_sync(kFull, event)) {
+            if (active) {
+                // ---------------- one RKF45 attempt (runge_kutta.rs:86-182, flattened retry loop) ----------------
+                double y_new[8];
+                bool accepted = false;
+                double acc_e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    y_new[i] = y[i];
+                    acc_e[i] = 0.0;
+                }
+                double* const kcol = s_k + tid;  // this lane's column of the [stage][component][thread] k store
+                double* kst = kcol;
+#pragma unroll 1
+                for (int s = 0; s < 6; ++s) {
+                    double tmp[8];
+                    switch (s) {
+                        case 0:
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) tmp[i] = y[i];
+                            break;
+                        case 1: stage_argument<G, 1>(kcol, y, tmp); break;
+                        case 2: stage_argument<G, 2>(kcol, y, tmp); break;
+                        case 3: stage_argument<G, 3>(kcol, y, tmp); break;
+                        case 4: stage_argument<G, 4>(kcol, y, tmp); break;
+                        default: stage_argument<G, 5>(kcol, y, tmp); break;
+                    }
+                    double d[8];
+                    geodesic_rhs<G>(S, C, tmp, d);
+                    const double ch = c_rk_ch[s], ct = c_rk_ct[s];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (Comp<G>::on(i)) {
+                            const double k = h_cur * d[i];
+                            if (s < 5 && Comp<G>::stored(i)) kst[Comp<G>::slot(i) * kTraceThreads] = k;
+                            y_new[i] = y_new[i] + ch * k;
+                            acc_e[i] = acc_e[i] + ct * k;
+                        }
+                    }
+                    kst += NC * kTraceThreads;
+                }
+                // truncation error: nalgebra's 8-accumulator dot product, (0,4) (1,5) (2,6) (3,7)
+                double e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) e[i] = Comp<G>::on(i) ? acc_e[i] * acc_e[i] : 0.0;
+                double res = (e[0] + e[4]);
+                res = res + (e[1] + e[5]);
+                res = res + (e[2] + e[6]);
+                res = res + (e[3] + e[7]);
+                const double err = sqrt(res);
+                ++R.attempts;
+                double h_proposed;
+#ifdef GRRT_FAST_MATH
+                // (epsilon/err)^(1/5) = q^(-1/5), q = err/epsilon: single-precision seed, then two steps of the
+                // division-free Newton iteration z <- z (1.2 - 0.2 q z^5) (error 3e^2 per step: 5e-6 -> 8e-11 -> < 1 ulp).
+                // Outside the seed's range (and for err = 0, inf, NaN) the exact path below decides.
+                const double q = err * S.inv_epsilon;
+                if (q > 1e-30 && q < 1e30) {
+                    double z = (double)exp2f(-0.2f * __log2f((float)q));
+                    const double mq = -0.2 * q;
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const double z2 = z * z;
+                        z = z * fma(mq, z2 * z2 * z, 1.2);
+                    }
+                    h_proposed = 0.9 * h_cur * z;
+                } else
+#endif
+                if (err > 0.0) h_proposed = 0.9 * h_cur * pow_glibc(pow_tab, S.epsilon / err, 1.0 / 5.0);
+                else h_proposed = h_cur * kHGrowthCap;
+                h_proposed = rclamp(fmin(h_proposed, h_cur * kHGrowthCap), kHMin, kHMax);
+                if (err > S.epsilon) {
+                    if (h_cur <= kHMin) {
+                        accepted = true;  // accept what we have at the minimum step
+                        h = h_cur;
+                    } else {
+                        h_cur = rclamp(h_proposed / 2.0, kHMin, kHMax);
+                        if (++R.retries >= kMaxRetryStep) {
+                            finish = GRRT_STOP_ERROR;
+                            ray_error = GRRT_RAYERR_RKF45_RETRIES;
+                        }
+                    }
+                } else {
+                    accepted = true;
+#ifdef GRRT_FAST_MATH
+                    h = (err * S.inv_epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
+#else
+                    h = (err / S.epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
+#endif
+                }
+                // ---------------- accepted step: chord tests against the objects, stop tests ----------------
+                if (accepted) {
+                    // far from every object and from the celestial sphere the chord needs no Cartesian end points and
+                    // the previous state (only read when a hit is shaded) is not kept
+                    const bool need_geo = segment_needs_cartesian<G>(S, y[1], y[2], y_new[1], y_new[2]);
+                    V3 prev_cart = v3(0.0, 0.0, 0.0);
+                    if (need_geo) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) s_yprev[i * kTraceThreads + tid] = y[i];
+                        prev_cart = R.prev_valid ? v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z)) : position_cartesian<G>(S, y);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = y_new[i];
+                    ++R.step;
+                    R.retries = 0;
+                    h_cur = rclamp(h, kHMin, kHMax);
+                    int st;
+                    if (need_geo) {
+                        const V3 cart = position_cartesian<G>(S, y);
+                        // geometric half of Objects::intersects (objects.rs:65-120): which objects become the nearest
+                        // hit when their turn comes; they are shaded, in this order, outside the loop
+                        double shortest = 1.7976931348623157e308;
+                        for (int k = 0; k < S.n_objects; ++k) {
+                            const DObject& o = S.obj[k];
+                            Hit hcur;
+                            bool hit;
+                            if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
+                            else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
+                            else hit = vol_intersects(o, prev_cart, cart, hcur);
+                            if (!hit) continue;
+                            const double distance = norm3(hcur.point - prev_cart);
+                            if (!(distance < shortest)) continue;
+                            shortest = distance;
+                            cand |= 1u << k;
+                        }
+                        CTX(CX_PREV_X) = cart.x;
+                        CTX(CX_PREV_Y) = cart.y;
+                        CTX(CX_PREV_Z) = cart.z;
+                        R.prev_valid = 1;
+                        st = should_stop<G>(S, y, cart, R.step);
+                    } else {
+                        R.prev_valid = 0;
+                        st = should_stop_inside<G>(S, y, R.step);
+                    }
+                    if (st != GRRT_STOP_NONE) finish = st;
+                    else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
+                }
+                event = cand != 0u || finish >= 0;
+            }
+        }
+
+        // ================= events =================
         auto push_hit = [&](const Cie& hit_color) {
             if (R.n_hits < kMaxHits) {
                 hits[R.n_hits++] = hit_color;
@@ -485,192 +629,75 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
             double alpha = rclamp(hit_color.a, 0.0, 1.0);
             CTX(CX_OPACITY) = alpha + CTX(CX_OPACITY) * (1.0 - alpha);  // scene.rs:149-150
         };
-        // ---------------- one RKF45 attempt (runge_kutta.rs:86-182, flattened retry loop) ----------------
-        if (active && !budget_empty) {
-            double y_new[8];
-            bool accepted = false;
-            double acc_e[8];
+        // ---------------- shading half of Objects::intersects for the candidates, in object order ----------------
+        int vol_k = -1;
+        if (cand) {
+            double yp[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                y_new[i] = y[i];
-                acc_e[i] = 0.0;
-            }
-            double* const kcol = s_k + tid;  // this lane's column of the [stage][component][thread] k store
-            double* kst = kcol;
-#pragma unroll 1
-            for (int s = 0; s < 6; ++s) {
-                double tmp[8];
-                switch (s) {
-                    case 0:
+            for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i * kTraceThreads + tid];
+            // the same two end points the loop tested (position_cartesian is a pure function of the state)
+            const V3 prev_cart = position_cartesian<G>(S, yp);
+            const V3 cart = position_cartesian<G>(S, y);
+            int best_k = -1;
+            double best_temperature = 0.0, best_redshift = 0.0;
+            Hit best;
+            best.u = best.v = best.t = 0.0;
+            best.point = best.dir = v3(0.0, 0.0, 0.0);
+            bool shading_error = false;
+            for (int k = 0; k < S.n_objects; ++k) {
+                if (!((cand >> k) & 1u)) continue;
+                const DObject& o = S.obj[k];
+                Hit hcur;
+                bool hit;
+                if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
+                else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
+                else hit = vol_intersects(o, prev_cart, cart, hcur);
+                if (!hit) continue;
+                // step_at_intersection (objects.rs:27-44): exact point, lerped momentum
+                double p0[4], p1[4], xs[4], ps[4];
+                momentum_from_state<G>(S, C, yp, p0);
+                momentum_from_state<G>(S, C, y, p1);
+                double s = 1.0 - hcur.t;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) tmp[i] = y[i];
+                for (int i = 0; i < 4; ++i) ps[i] = s * p0[i] + hcur.t * p1[i];
+                cartesian_to_native<G>(S, hcur.point, xs);
+                double vel[4];
+                if (o.kind == GRRT_OBJ_SPHERE) {
+                    stationary_velocity<G>(S, xs, vel);
+                } else if (!circular_orbit_velocity<G>(S, xs, vel)) {
+                    shading_error = true;
+                    ray_error = GRRT_RAYERR_NO_CIRCULAR_ORBIT;
+                    break;
+                }
+                double emitter_energy = inner_product<G>(S, xs, vel, ps);
+                best_redshift = (GeomTraits<G>::sig0 * CTX(CX_FREQ_E)) / (GeomTraits<G>::sig0 * emitter_energy);
+                if (o.kind == GRRT_OBJ_SPHERE) {
+                    best_temperature = o.sphere_temperature;
+                } else {
+                    int terr = compute_temperature(o.temp, radial_coordinate_cart<G>(S, hcur.point), best_temperature);
+                    if (terr) {
+                        shading_error = true;
+                        ray_error = terr;
                         break;
-                    case 1: stage_argument<G, 1>(kcol, y, tmp); break;
-                    case 2: stage_argument<G, 2>(kcol, y, tmp); break;
-                    case 3: stage_argument<G, 3>(kcol, y, tmp); break;
-                    case 4: stage_argument<G, 4>(kcol, y, tmp); break;
-                    default: stage_argument<G, 5>(kcol, y, tmp); break;
-                }
-                double d[8];
-                geodesic_rhs<G>(S, C, tmp, d);
-                const double ch = c_rk_ch[s], ct = c_rk_ct[s];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (Comp<G>::on(i)) {
-                        const double k = h_cur * d[i];
-                        if (s < 5 && Comp<G>::stored(i)) kst[Comp<G>::slot(i) * kTraceThreads] = k;
-                        y_new[i] = y_new[i] + ch * k;
-                        acc_e[i] = acc_e[i] + ct * k;
                     }
                 }
-                kst += NC * kTraceThreads;
+                best = hcur;
+                best_k = k;
             }
-            // truncation error: nalgebra's 8-accumulator dot product, (0,4) (1,5) (2,6) (3,7)
-            double e[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = Comp<G>::on(i) ? acc_e[i] * acc_e[i] : 0.0;
-            double res = (e[0] + e[4]);
-            res = res + (e[1] + e[5]);
-            res = res + (e[2] + e[6]);
-            res = res + (e[3] + e[7]);
-            const double err = sqrt(res);
-            ++R.attempts;
-            double h_proposed;
-#ifdef GRRT_FAST_MATH
-            // (epsilon/err)^(1/5) = q^(-1/5), q = err/epsilon: single-precision seed, then two steps of the
-            // division-free Newton iteration z <- z (1.2 - 0.2 q z^5) (error 3e^2 per step: 5e-6 -> 8e-11 -> < 1 ulp).
-            // Outside the seed's range (and for err = 0, inf, NaN) the exact path below decides.
-            const double q = err * S.inv_epsilon;
-            if (q > 1e-30 && q < 1e30) {
-                double z = (double)exp2f(-0.2f * __log2f((float)q));
-                const double mq = -0.2 * q;
-#pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                    const double z2 = z * z;
-                    z = z * fma(mq, z2 * z2 * z, 1.2);
-                }
-                h_proposed = 0.9 * h_cur * z;
-            } else
-#endif
-            if (err > 0.0) h_proposed = 0.9 * h_cur * pow_glibc(pow_tab, S.epsilon / err, 1.0 / 5.0);
-            else h_proposed = h_cur * kHGrowthCap;
-            h_proposed = rclamp(fmin(h_proposed, h_cur * kHGrowthCap), kHMin, kHMax);
-            if (err > S.epsilon) {
-                if (h_cur <= kHMin) {
-                    accepted = true;  // accept what we have at the minimum step
-                    h = h_cur;
+            if (shading_error) {
+                finish = GRRT_STOP_ERROR;  // `?` in Objects::intersects: the whole pixel fails (raytracer.rs:230-239)
+            } else if (best_k >= 0) {
+                const DObject& o = S.obj[best_k];
+                if (HAS_VOL && o.kind == GRRT_OBJ_VOLUMETRIC_DISC) {
+                    vol_k = best_k;  // shaded below by the whole warp
+                    CTX(CX_VOL_PX) = best.point.x;
+                    CTX(CX_VOL_PY) = best.point.y;
+                    CTX(CX_VOL_PZ) = best.point.z;
+                    CTX(CX_VOL_DX) = best.dir.x;
+                    CTX(CX_VOL_DY) = best.dir.y;
+                    CTX(CX_VOL_DZ) = best.dir.z;
                 } else {
-                    h_cur = rclamp(h_proposed / 2.0, kHMin, kHMax);
-                    if (++R.retries >= kMaxRetryStep) {
-                        finish = GRRT_STOP_ERROR;
-                        ray_error = GRRT_RAYERR_RKF45_RETRIES;
-                    }
-                }
-            } else {
-                accepted = true;
-#ifdef GRRT_FAST_MATH
-                h = (err * S.inv_epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
-#else
-                h = (err / S.epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
-#endif
-            }
-            // ---------------- accepted step: objects on the chord prev -> cur, stop tests ----------------
-            if (accepted) {
-                // far from every object and from the celestial sphere the chord needs no Cartesian end points and the
-                // previous state (only read when a hit is shaded) is not kept
-                const bool need_geo = segment_needs_cartesian<G>(S, y[1], y[2], y_new[1], y_new[2]);
-                V3 prev_cart = v3(0.0, 0.0, 0.0);
-                if (need_geo) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) s_yprev[i * kTraceThreads + tid] = y[i];
-                    prev_cart = R.prev_valid ? v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z)) : position_cartesian<G>(S, y);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = y_new[i];
-                ++R.step;
-                R.retries = 0;
-                h_cur = rclamp(h, kHMin, kHMax);
-                if (need_geo) {
-                    const V3 cart = position_cartesian<G>(S, y);
-                    // Objects::intersects (objects.rs:65-120)
-                    double shortest = 1.7976931348623157e308;
-                    int best_k = -1;
-                    double best_temperature = 0.0, best_redshift = 0.0;
-                    Hit best;
-                    best.u = best.v = best.t = 0.0;
-                    best.point = best.dir = v3(0.0, 0.0, 0.0);
-                    for (int k = 0; k < S.n_objects; ++k) {
-                        const DObject& o = S.obj[k];
-                        Hit hcur;
-                        bool hit;
-                        if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
-                        else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
-                        else hit = vol_intersects(o, prev_cart, cart, hcur);
-                        if (!hit) continue;
-                        double distance = norm3(hcur.point - prev_cart);
-                        if (!(distance < shortest)) continue;
-                        shortest = distance;
-                        // step_at_intersection (objects.rs:27-44): exact point, lerped momentum
-                        double yp[8], p0[4], p1[4], xs[4], ps[4];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i * kTraceThreads + tid];
-                        momentum_from_state<G>(S, C, yp, p0);
-                        momentum_from_state<G>(S, C, y, p1);
-                        double s = 1.0 - hcur.t;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) ps[i] = s * p0[i] + hcur.t * p1[i];
-                        cartesian_to_native<G>(S, hcur.point, xs);
-                        double vel[4];
-                        if (o.kind == GRRT_OBJ_SPHERE) {
-                            stationary_velocity<G>(S, xs, vel);
-                        } else if (!circular_orbit_velocity<G>(S, xs, vel)) {
-                            finish = GRRT_STOP_ERROR;
-                            ray_error = GRRT_RAYERR_NO_CIRCULAR_ORBIT;
-                            break;
-                        }
-                        double emitter_energy = inner_product<G>(S, xs, vel, ps);
-                        best_redshift = (GeomTraits<G>::sig0 * CTX(CX_FREQ_E)) / (GeomTraits<G>::sig0 * emitter_energy);
-                        if (o.kind == GRRT_OBJ_SPHERE) {
-                            best_temperature = o.sphere_temperature;
-                        } else {
-                            int terr = compute_temperature(o.temp, radial_coordinate_cart<G>(S, hcur.point), best_temperature);
-                            if (terr) {
-                                finish = GRRT_STOP_ERROR;
-                                ray_error = terr;
-                                break;
-                            }
-                        }
-                        best = hcur;
-                        best_k = k;
-                    }
-                    if (finish != GRRT_STOP_ERROR) {
-                        if (best_k >= 0) {
-                            const DObject& o = S.obj[best_k];
-                            if (HAS_VOL && o.kind == GRRT_OBJ_VOLUMETRIC_DISC) {
-                                vol_k = best_k;  // shaded below by the whole warp
-                                CTX(CX_VOL_PX) = best.point.x;
-                                CTX(CX_VOL_PY) = best.point.y;
-                                CTX(CX_VOL_PZ) = best.point.z;
-                                CTX(CX_VOL_DX) = best.dir.x;
-                                CTX(CX_VOL_DY) = best.dir.y;
-                                CTX(CX_VOL_DZ) = best.dir.z;
-                            } else {
-                                push_hit(texture_color(S, o.tex, best.u, best.v, best_temperature, best_redshift));
-                            }
-                        }
-                        CTX(CX_PREV_X) = cart.x;
-                        CTX(CX_PREV_Y) = cart.y;
-                        CTX(CX_PREV_Z) = cart.z;
-                        R.prev_valid = 1;
-                        st = should_stop<G>(S, y, cart, R.step);
-                    }
-                } else {
-                    R.prev_valid = 0;
-                    st = should_stop_inside<G>(S, y, R.step);
-                }
-                if (finish != GRRT_STOP_ERROR) {  // terminal event of the accepted step
-                    if (st != GRRT_STOP_NONE) finish = st;
-                    else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
+                    push_hit(texture_color(S, o.tex, best.u, best.v, best_temperature, best_redshift));
                 }
             }
         }
