@@ -63,8 +63,9 @@ def build(force=False, verbose=False):
                 cmd += ["-fmad=" + FMAD[src]] + (["-Xptxas", "-v"] if verbose else [])
                 if os.environ.get("GRRT_MB"):   # experiment knob: resident CTAs/SM the register allocator targets
                     cmd += ["-DGRRT_MB=" + os.environ["GRRT_MB"]]
-                if os.environ.get("GRRT_MBV"):
-                    cmd += ["-DGRRT_MBV=" + os.environ["GRRT_MBV"]]
+                for knob in ("GRRT_MBV", "GRRT_MB_BL"):
+                    if os.environ.get(knob):
+                        cmd += ["-D%s=%s" % (knob, os.environ[knob])]
             else:
                 cmd += ["-Xcompiler", "-ffp-contract=off"]
             jobs.append(cmd)

@@ -11,6 +11,9 @@
 
 namespace GRRT_NS {
 
+#ifndef GRRT_MB_BL
+#define GRRT_MB_BL 5  // KerrBL: 96 registers, 5 CTAs/SM measured faster than 4 (and than 6); Schwarzschild prefers 4
+#endif
 #ifndef GRRT_MBV
 #define GRRT_MBV 3  // resident CTAs/SM the volumetric kernels are register-allocated for
 #endif
@@ -20,7 +23,7 @@ int launch_trace_v(const DScene& s, const TraceArgs& a, const TraceLaunch& l) {
         case GRRT_GEOM_EUCLIDEAN: return launch_trace_t<GRRT_GEOM_EUCLIDEAN, V, (V ? GRRT_MBV : 4)>(s, a, l);
         case GRRT_GEOM_EUCLIDEAN_SPHERICAL: return launch_trace_t<GRRT_GEOM_EUCLIDEAN_SPHERICAL, V, (V ? GRRT_MBV : 4)>(s, a, l);
         case GRRT_GEOM_SCHWARZSCHILD: return launch_trace_t<GRRT_GEOM_SCHWARZSCHILD, V, (V ? GRRT_MBV : GRRT_MB)>(s, a, l);
-        case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V, (V ? GRRT_MBV : GRRT_MB)>(s, a, l);
+        case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V, (V ? GRRT_MBV : GRRT_MB_BL)>(s, a, l);
 #ifdef GRRT_WITH_KERR_SCHILD
         case GRRT_GEOM_KERR: return launch_trace_t<GRRT_GEOM_KERR, V, (V ? 2 : 3)>(s, a, l);
 #endif
