@@ -178,6 +178,8 @@ class Context:
         fc = 0 if from_col is None else from_col
         tr = sc.camera.rows if to_row is None else to_row
         tc = sc.camera.cols if to_col is None else to_col
+        if tr < fr or tc < fc:  # what grrt_render answers; raised here before any buffer is sized from it
+            raise GrrtError(abi.ERR_INVALID_ARGUMENT, "inverted section")
         n = (tr - fr) * (tc - fc)
         if out is not None:
             xyza, cls, stop, steps = out["xyza"], out["ray_class"], out["stop"], out["steps"]
