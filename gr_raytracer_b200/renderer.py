@@ -47,6 +47,15 @@ class DeviceEngine:
         self.device = torch.device("cuda", ctx.device)
         self.counters = torch.zeros(16, dtype=torch.int64, device=self.device)
 
+    def reupload(self, scene=None):
+        """Uploads the scene again (host -> device), replacing the resident copy: one frame's input transfer."""
+        if scene is not None:
+            self.scene = scene
+        old = self.dscene
+        self.dscene = self.ctx.upload(self.scene)
+        if old is not None:
+            self.ctx.free_scene(old)
+
     def close(self):
         if self.dscene is not None:
             self.ctx.free_scene(self.dscene)
@@ -95,8 +104,11 @@ class FrameRenderer:
             self.my_items = torch.from_numpy(ids.astype(np.int32)).to(self.xyza.device)
             self.n_mine = int(ids.size)
             self.max_items = max(int(tile_interleaved_items(self.W, self.H, r, world).size) for r in range(world))
-            self.all_items = [torch.from_numpy(tile_interleaved_items(self.W, self.H, r, world).astype(np.int64)).to(self.xyza.device)
-                              for r in range(world)]
+            # where every slot of the gathered [world, max_items] buffers goes in the frame (padding slots dropped)
+            per_rank = [tile_interleaved_items(self.W, self.H, r, world).astype(np.int64) for r in range(world)]
+            src = np.concatenate([r * self.max_items + np.arange(ids_r.size, dtype=np.int64) for r, ids_r in enumerate(per_rank)])
+            self.gather_src = torch.from_numpy(src).to(self.xyza.device)
+            self.gather_dst = torch.from_numpy(np.concatenate(per_rank)).to(self.xyza.device)
             m = self.max_items
             self.loc_xyza = engine.new((m, 4), torch.float64)
             self.loc_cls = engine.new((m,), torch.uint8)
@@ -120,12 +132,10 @@ class FrameRenderer:
             meta = torch.stack((self.loc_cls, self.loc_stop), dim=1)
             self._all_gather(self.gat_xyza.view(-1, 4), self.loc_xyza)
             self._all_gather(self.gat_meta.view(-1, 2), meta)
-            for r in range(self.world):
-                idx = self.all_items[r]
-                k = idx.numel()
-                self.xyza.index_copy_(0, idx, self.gat_xyza[r, :k])
-                self.cls.index_copy_(0, idx, self.gat_meta[r, :k, 0])
-                self.stop.index_copy_(0, idx, self.gat_meta[r, :k, 1])
+            self.xyza.index_copy_(0, self.gather_dst, self.gat_xyza.view(-1, 4).index_select(0, self.gather_src))
+            meta_all = self.gat_meta.view(-1, 2).index_select(0, self.gather_src)
+            self.cls.index_copy_(0, self.gather_dst, meta_all[:, 0].contiguous())
+            self.stop.index_copy_(0, self.gather_dst, meta_all[:, 1].contiguous())
         n_sel = 0
         min_lum = 0.0
         if ad.enabled or ad.show_sampling_mask:
