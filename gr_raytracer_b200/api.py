@@ -54,6 +54,9 @@ def lib():
                                        C.POINTER(C.c_int32)]
     L.grrt_scene_upload.argtypes = [vp, scene_p, C.POINTER(vp)]
     L.grrt_scene_free.argtypes = [vp, vp]
+    L.grrt_scene_set_camera.argtypes = [vp, vp, C.POINTER(abi.GrrtCamera)]
+    L.grrt_render_resident.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp, u8p, u8p, u32p,
+                                       C.POINTER(abi.GrrtStats)]
     L.grrt_trace_items_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp]
     L.grrt_select_mask_device.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, dp, vp]
@@ -74,6 +77,7 @@ def lib():
         L.grrt_host_scene_get.argtypes = [vp]
         L.grrt_host_scene_get.restype = scene_p
         L.grrt_host_scene_free.argtypes = [vp]
+        L.grrt_host_scene_set_camera.argtypes = [vp, C.POINTER(abi.GrrtCliOpts), C.c_char_p, C.c_size_t]
         L.grrt_host_ray_at.argtypes = [C.POINTER(abi.GrrtGeometry), dp, dp, dp, dp, C.c_char_p, C.c_size_t]
         L.grrt_host_write_ray_csv.argtypes = [C.POINTER(abi.GrrtGeometry), C.POINTER(abi.GrrtStep), C.c_uint64, C.c_char_p]
         L.grrt_host_write_png_rgb8.argtypes = [C.c_char_p, u8p, C.c_uint32, C.c_uint32]
@@ -125,6 +129,20 @@ class HostScene:
     def c(self):
         return self.ptr.contents
 
+    def set_camera(self, **overrides):
+        """New camera for the assembled scene (camera_position, phi, theta, psi, width, height of the CLI options);
+        textures and look-up tables are kept.  One call per animation frame."""
+        for k, v in overrides.items():
+            if k == "camera_position":
+                for i in range(3):
+                    self.opts.camera_position[i] = float(v[i])
+            else:
+                setattr(self.opts, k, v)
+        err = C.create_string_buffer(1024)
+        rc = lib().grrt_host_scene_set_camera(self._h, C.byref(self.opts), err, len(err))
+        if rc:
+            raise GrrtError(rc, err.value.decode(errors="replace"))
+
     def close(self):
         if getattr(self, "_h", None):
             lib().grrt_host_scene_free(self._h)
@@ -174,10 +192,23 @@ class Context:
         """`out` (optional): dict of preallocated C-contiguous host arrays xyza[n,4] f64, ray_class[n] u8, stop[n] u8,
         steps[n] u32 -- e.g. views of pinned torch tensors -- to avoid per-call allocation and pageable copies."""
         sc = _scene_struct(scene)
+        call = lambda *a: lib().grrt_render(self._h, _scene_ptr(scene), *a)
+        return self._render(call, sc.camera.rows, sc.camera.cols, from_row, from_col, to_row, to_col, out)
+
+    def render_resident(self, dscene, rows, cols, from_row=None, from_col=None, to_row=None, to_col=None, out=None):
+        """grrt_render_resident: the frame of an uploaded scene (see upload / set_camera) into host buffers."""
+        call = lambda *a: lib().grrt_render_resident(self._h, dscene, *a)
+        return self._render(call, rows, cols, from_row, from_col, to_row, to_col, out)
+
+    def set_camera(self, dscene, camera):
+        """Replaces the camera of an uploaded scene (`camera`: abi.GrrtCamera, e.g. HostScene.c.camera)."""
+        self._check(lib().grrt_scene_set_camera(self._h, dscene, C.byref(camera)))
+
+    def _render(self, call, rows, cols, from_row, from_col, to_row, to_col, out):
         fr = 0 if from_row is None else from_row
         fc = 0 if from_col is None else from_col
-        tr = sc.camera.rows if to_row is None else to_row
-        tc = sc.camera.cols if to_col is None else to_col
+        tr = rows if to_row is None else to_row
+        tc = cols if to_col is None else to_col
         if tr < fr or tc < fc:  # what grrt_render answers; raised here before any buffer is sized from it
             raise GrrtError(abi.ERR_INVALID_ARGUMENT, "inverted section")
         n = (tr - fr) * (tc - fc)
@@ -190,10 +221,8 @@ class Context:
             stop = np.zeros(n, dtype=np.uint8)
             steps = np.zeros(n, dtype=np.uint32)
         stats = abi.GrrtStats()
-        self._check(lib().grrt_render(self._h, _scene_ptr(scene), fr, fc, tr, tc,
-                                      xyza.ctypes.data_as(abi.c_double_p), cls.ctypes.data_as(abi.c_uint8_p),
-                                      stop.ctypes.data_as(abi.c_uint8_p), steps.ctypes.data_as(C.POINTER(C.c_uint32)),
-                                      C.byref(stats)))
+        self._check(call(fr, fc, tr, tc, xyza.ctypes.data_as(abi.c_double_p), cls.ctypes.data_as(abi.c_uint8_p),
+                         stop.ctypes.data_as(abi.c_uint8_p), steps.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(stats)))
         shape = (tr - fr, tc - fc)
         return dict(xyza=xyza.reshape(shape + (4,)), ray_class=cls.reshape(shape), stop=stop.reshape(shape),
                     steps=steps.reshape(shape), stats=stats.as_dict())

@@ -358,6 +358,28 @@ unsigned long long grrt_kernel_launch_count(const GrrtCtx* ctx) { return ctx ? c
 
 const char* grrt_last_error(const GrrtCtx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
 
+namespace {
+void set_camera(DScene& s, const GrrtCamera& cam) {
+    for (int i = 0; i < 4; ++i) {
+        s.cam_pos[i] = cam.position[i];
+        s.cam_vel[i] = cam.velocity[i];
+        for (int j = 0; j < 4; ++j) s.tet[i][j] = cam.tetrad[i][j];
+    }
+    s.cam_rows = (double)cam.rows;
+    s.cam_cols = (double)cam.cols;
+    s.cam_scale = 2.0 * std::tan(cam.alpha / 2.0) / (double)cam.rows;  // camera.rs:217-224
+    s.cam_hand = cam.spatial_handedness;
+    s.cam_sig = cam.spatial_signature;
+}
+}  // namespace
+
+int grrt_scene_set_camera(GrrtCtx* ctx, GrrtDeviceScene* ds, const GrrtCamera* camera) {
+    if (!ctx || !ds || !camera) return GRRT_ERR_INVALID_ARGUMENT;
+    if (camera->rows <= 0 || camera->cols <= 0) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "camera has no pixels");
+    set_camera(ds->s, *camera);  // the scene block travels as a kernel argument: nothing to copy to the device
+    return GRRT_OK;
+}
+
 int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) {
     if (!ctx || !sc || !out) return GRRT_ERR_INVALID_ARGUMENT;
     *out = nullptr;
@@ -385,16 +407,7 @@ int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) 
         s.r_plus_eps = rp + s.heps;
     }
     s.n_objects = (int)sc->n_objects;
-    for (int i = 0; i < 4; ++i) {
-        s.cam_pos[i] = sc->camera.position[i];
-        s.cam_vel[i] = sc->camera.velocity[i];
-        for (int j = 0; j < 4; ++j) s.tet[i][j] = sc->camera.tetrad[i][j];
-    }
-    s.cam_rows = (double)sc->camera.rows;
-    s.cam_cols = (double)sc->camera.cols;
-    s.cam_scale = 2.0 * std::tan(sc->camera.alpha / 2.0) / (double)sc->camera.rows;  // camera.rs:217-224
-    s.cam_hand = sc->camera.spatial_handedness;
-    s.cam_sig = sc->camera.spatial_signature;
+    set_camera(s, sc->camera);
     s.max_steps = sc->integration.max_steps;
     s.max_radius_sq = sc->integration.max_radius * sc->integration.max_radius;  // integrator.rs:62
     s.step_size = sc->integration.step_size;
@@ -629,11 +642,19 @@ int grrt_render(GrrtCtx* ctx, const GrrtScene* scene, uint32_t from_row, uint32_
     GrrtDeviceScene* ds = nullptr;
     int rc = grrt_scene_upload(ctx, scene, &ds);
     if (rc) return rc;
-    struct Guard {
-        GrrtCtx* c;
-        GrrtDeviceScene* d;
-        ~Guard() { grrt_scene_free(c, d); }
-    } guard{ctx, ds};
+    rc = grrt_render_resident(ctx, ds, from_row, from_col, to_row, to_col, xyza_out, ray_class_out, stop_reason_out, steps_out,
+                              stats);
+    grrt_scene_free(ctx, ds);
+    return rc;
+}
+
+int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_row, uint32_t from_col, uint32_t to_row,
+                         uint32_t to_col, double* xyza_out, uint8_t* ray_class_out, uint8_t* stop_reason_out,
+                         uint32_t* steps_out, GrrtStats* stats) {
+    if (!ctx || !ds || !xyza_out) return GRRT_ERR_INVALID_ARGUMENT;
+    if (to_row < from_row || to_col < from_col) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "inverted section");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = GRRT_OK;
     const uint32_t W = to_col - from_col, H = to_row - from_row;
     const size_t n = (size_t)W * H;
     GrrtStats st;
@@ -662,7 +683,7 @@ int grrt_render(GrrtCtx* ctx, const GrrtScene* scene, uint32_t from_row, uint32_
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ev[1], s));
     st.rays_base = n;
-    const GrrtAdaptive& ad = scene->adaptive;
+    const GrrtAdaptive& ad = ds->adaptive;
     uint32_t n_sel = 0;
     CUDA_TRY(ctx, cudaEventRecord(ev[2], s));
     if (ad.enabled || ad.show_sampling_mask) {  // raytracer.rs:184

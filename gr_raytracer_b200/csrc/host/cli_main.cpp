@@ -6,9 +6,17 @@
 //        render [--filename render.png] [--from-row .. --from-col .. --to-row .. --to-col ..]
 //      | render-ray --row R --col C [--filename rendered-ray.csv]
 //      | render-ray-at --position x,y,z --direction x,y,z [--filename rendered-ray-at.csv]
+//      | render-frames --camera-positions positions.csv [--output-pattern frame_%05d.png] [--first K --stride S --count N]
 //
-// Extra (not in the reference): --resource-root DIR (prefix for relative texture paths), --device N.
+// Extra (not in the reference): --resource-root DIR (prefix for relative texture paths), --device N, and
+// render-frames: the reference's camera fly-through (scripts/Readme.md) runs the binary once per camera position;
+// here one process keeps the scene resident on the GPU, replaces only the camera per frame and encodes frame k on a
+// host thread while the GPU renders frame k+1.  positions.csv: one `x,y,z[,phi,theta,psi]` per line (other lines
+// are skipped); frames first, first+stride, ... are rendered, so N processes with --first r --stride N --device r
+// split a movie over N GPUs.
 #include <chrono>
+#include <fstream>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -48,7 +56,8 @@ bool ends_with(const std::string& s, const char* suf) {
 int main(int argc, char** argv) {
     GrrtCliOpts opts;
     grrt_cli_opts_default(&opts);
-    std::string config_file, action, filename, resource_root;
+    std::string config_file, action, filename, resource_root, positions_file, output_pattern = "frame_%05d.png";
+    long long first_frame = 0, frame_stride = 1, frame_count = -1;
     long long from_row = -1, from_col = -1, to_row = -1, to_col = -1, ray_row = -1, ray_col = -1;
     std::vector<double> at_pos, at_dir;
     int device = 0;
@@ -104,11 +113,16 @@ int main(int argc, char** argv) {
         else if (flag == "--col") ray_col = std::atoll(value(i, flag).c_str());
         else if (flag == "--position" || flag == "-p") at_pos = parse_list(value(i, flag), "--position");
         else if (flag == "--direction" || flag == "-d") at_dir = parse_list(value(i, flag), "--direction");
-        else if (a == "render" || a == "render-ray" || a == "render-ray-at") action = a;
+        else if (flag == "--camera-positions") positions_file = value(i, flag);
+        else if (flag == "--output-pattern") output_pattern = value(i, flag);
+        else if (flag == "--first") first_frame = std::atoll(value(i, flag).c_str());
+        else if (flag == "--stride") frame_stride = std::atoll(value(i, flag).c_str());
+        else if (flag == "--count") frame_count = std::atoll(value(i, flag).c_str());
+        else if (a == "render" || a == "render-ray" || a == "render-ray-at" || a == "render-frames") action = a;
         else if (a == "blackbody" || a == "blackbody-spectrum") die("subcommand '" + a + "' is not part of the geodesic path and is not provided by grrt");
         else die("unexpected argument '" + a + "'");
     }
-    if (action.empty()) die("a subcommand is required: render | render-ray | render-ray-at");
+    if (action.empty()) die("a subcommand is required: render | render-ray | render-ray-at | render-frames");
     if (config_file.empty()) die("Invalid configuration: Config file is required for this action");
 
     auto t0 = std::chrono::steady_clock::now();
@@ -121,7 +135,68 @@ int main(int argc, char** argv) {
     GrrtCtx* ctx = nullptr;
     if (grrt_init(device, &ctx) != 0) die("no usable CUDA device (sm_100): grrt has no CPU fallback");
 
-    if (action == "render") {
+    if (action == "render-frames") {
+        if (positions_file.empty()) die("render-frames needs --camera-positions");
+        if (frame_stride <= 0 || first_frame < 0) die("Invalid configuration: --first must be >= 0 and --stride > 0");
+        std::vector<std::vector<double>> cams;  // x,y,z[,phi,theta,psi]
+        {
+            std::ifstream in(positions_file);
+            if (!in) die("I/O error: cannot read " + positions_file);
+            std::string line;
+            while (std::getline(in, line)) {
+                std::vector<double> v;
+                size_t p = 0;
+                bool ok = !line.empty();
+                while (ok && p <= line.size()) {
+                    size_t q = line.find(',', p);
+                    if (q == std::string::npos) q = line.size();
+                    std::string tok = line.substr(p, q - p);
+                    char* end = nullptr;
+                    double x = std::strtod(tok.c_str(), &end);
+                    while (end && (*end == ' ' || *end == '\r' || *end == '\t')) ++end;
+                    if (tok.empty() || !end || *end != '\0') ok = false;
+                    else v.push_back(x);
+                    p = q + 1;
+                }
+                if (ok && (v.size() == 3 || v.size() == 6)) cams.push_back(v);  // header / comment lines are skipped
+            }
+        }
+        if (cams.empty()) die("Invalid configuration: no camera positions in " + positions_file);
+        GrrtDeviceScene* ds = nullptr;
+        if (grrt_scene_upload(ctx, scene, &ds)) die(grrt_last_error(ctx));
+        const uint32_t W = (uint32_t)scene->camera.cols, H = (uint32_t)scene->camera.rows;
+        const size_t n = (size_t)W * H;
+        std::vector<double> xyza(4 * n);
+        std::vector<uint8_t> rgb[2] = {std::vector<uint8_t>(3 * n), std::vector<uint8_t>(3 * n)};
+        std::thread writer;
+        std::string write_error;
+        long long done = 0;
+        double device_ms = 0.0;
+        for (long long k = first_frame; k < (long long)cams.size() && (frame_count < 0 || done < frame_count); k += frame_stride, ++done) {
+            const std::vector<double>& c = cams[(size_t)k];
+            for (int j = 0; j < 3; ++j) opts.camera_position[j] = c[j];
+            if (c.size() == 6) { opts.phi = c[3]; opts.theta = c[4]; opts.psi = c[5]; }
+            if (grrt_host_scene_set_camera(hs, &opts, err, sizeof err)) die(std::string("frame ") + std::to_string(k) + ": " + err);
+            if (grrt_scene_set_camera(ctx, ds, &scene->camera)) die(grrt_last_error(ctx));
+            GrrtStats st;
+            if (grrt_render_resident(ctx, ds, 0, 0, H, W, xyza.data(), nullptr, nullptr, nullptr, &st)) die(grrt_last_error(ctx));
+            device_ms += st.device_ms_total;
+            std::vector<uint8_t>& buf = rgb[done & 1];
+            if (grrt_tonemap(ctx, xyza.data(), n, opts.tone_mapping, 1.0, buf.data())) die(grrt_last_error(ctx));
+            char name[4096];
+            std::snprintf(name, sizeof name, output_pattern.c_str(), (int)k);
+            if (writer.joinable()) writer.join();  // frame k-1 was encoding while this one rendered
+            if (!write_error.empty()) die(write_error);
+            std::string path = name;
+            writer = std::thread([&buf, &write_error, path, W, H] {
+                if (grrt_host_write_png_rgb8(path.c_str(), buf.data(), W, H)) write_error = "I/O error: cannot write " + path;
+            });
+        }
+        if (writer.joinable()) writer.join();
+        if (!write_error.empty()) die(write_error);
+        grrt_scene_free(ctx, ds);
+        std::fprintf(stderr, "[grrt] rendered %lld frames (%ux%u), device %.1f ms per frame\n", done, W, H, done ? device_ms / done : 0.0);
+    } else if (action == "render") {
         if (filename.empty()) filename = "render.png";
         uint32_t fr = from_row < 0 ? 0 : (uint32_t)from_row, fc = from_col < 0 ? 0 : (uint32_t)from_col;
         uint32_t tr = to_row < 0 ? (uint32_t)scene->camera.rows : (uint32_t)to_row;

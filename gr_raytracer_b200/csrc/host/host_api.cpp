@@ -73,6 +73,14 @@ int grrt_host_scene_from_toml_file(const char* toml_path, const char* resource_r
 const GrrtScene* grrt_host_scene_get(const GrrtHostScene* hs) { return hs ? &hs->data.scene : nullptr; }
 void grrt_host_scene_free(GrrtHostScene* hs) { delete hs; }
 
+int grrt_host_scene_set_camera(GrrtHostScene* hs, const GrrtCliOpts* opts, char* err, size_t err_len) {
+    if (!hs || !opts) return GRRT_ERR_INVALID_ARGUMENT;
+    std::string msg;
+    int rc = update_camera(hs->data, *opts, msg);
+    if (rc) set_err(err, err_len, msg);
+    return rc;
+}
+
 int grrt_host_ray_at(const GrrtGeometry* geometry, const double position_cartesian[3], const double direction_cartesian[3],
                      double pos_out[4], double mom_out[4], char* err, size_t err_len) {
     if (!geometry || !position_cartesian || !direction_cartesian || !pos_out || !mom_out) return GRRT_ERR_INVALID_ARGUMENT;

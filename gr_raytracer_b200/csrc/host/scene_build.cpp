@@ -659,6 +659,51 @@ void enum_variant(const TomlValue& v, const char* what, std::string& name, const
 }  // namespace
 
 // =========================================================================================================
+// resolve_camera_velocity + assert_future_directed (cli/shared.rs:23-86)
+Vec4 resolve_camera_velocity(const HostGeometry& geo, const Vec4& pos, const std::string& mode, const double explicit_components[4]) {
+    Vec4 vel;
+    if (mode == "StaticObserver") vel = geo.stationary_velocity(pos);
+    else if (mode == "Zamo") vel = geo.zamo_velocity(pos);
+    else if (mode == "Explicit") {
+        for (int i = 0; i < 4; ++i) vel[i] = explicit_components[i];
+        double n = geo.inner(pos, vel, vel);
+        if (std::fabs(n - geo.sig0()) > 1e-6) bad(GRRT_ERR_INVALID_CONFIGURATION, "Explicit camera_velocity is not normalized");
+    } else {
+        bad(GRRT_ERR_TOML, "unknown variant `" + mode + "` for camera_velocity");
+    }
+    Vec4 tt = geo.tetrad_at(pos).t;
+    double orientation = geo.sig0() * geo.inner(pos, tt, vel);
+    if (!(std::isfinite(vel[0]) && 1.0 * orientation > 0.0))
+        bad(GRRT_ERR_INVALID_CONFIGURATION, "camera four-velocity has wrong time orientation");
+    return vel;
+}
+
+// Camera::new (camera.rs:151-196): alpha = PI/4, rows = height, cols = width
+void make_camera(const HostGeometry& geo, const Vec4& pos, const Vec4& vel, const GrrtCliOpts& opts, GrrtCamera& cam) {
+    Frame T0 = geo.tetrad_at(pos);
+    if (!geo.orthonormal(pos, T0)) bad(GRRT_ERR_TETRAD_NOT_ORTHONORMAL, "Tetrad is not orthonormal");
+    Vec4 a1, b1, z, a2, x, y;
+    rotate_pair(T0.x, T0.y, opts.phi, a1, b1);
+    rotate_pair(T0.z, a1, opts.theta, z, a2);
+    rotate_pair(a2, b1, opts.psi, x, y);
+    Mat4 L = geo.lorentz(pos, vel);
+    Frame T{matvec(L, T0.t), matvec(L, x), matvec(L, y), matvec(L, z)};
+    if (!geo.orthonormal(pos, T)) bad(GRRT_ERR_TETRAD_NOT_ORTHONORMAL, "Tetrad is not orthonormal");
+    for (int i = 0; i < 4; ++i) {
+        cam.position[i] = pos[i];
+        cam.velocity[i] = vel[i];
+        cam.tetrad[0][i] = T.t[i];
+        cam.tetrad[1][i] = T.x[i];
+        cam.tetrad[2][i] = T.y[i];
+        cam.tetrad[3][i] = T.z[i];
+    }
+    cam.alpha = PI / 4.0;
+    cam.rows = opts.height;
+    cam.cols = opts.width;
+    cam.spatial_signature = -geo.sig0();
+    cam.spatial_handedness = geo.handedness(pos, T);
+}
+
 struct SceneBuilder {
     HostSceneData& hs;
     const GrrtCliOpts& opts;
@@ -826,27 +871,17 @@ struct SceneBuilder {
 
         // camera chart, four-velocity, future-directedness (cli/<geometry>.rs, cli/shared.rs:23-86)
         Vec4 pos = geo.camera_position_native(opts.camera_position);
-        Vec4 vel;
         {
-            std::string mode = "StaticObserver";
+            hs.camera_velocity_mode = "StaticObserver";
             const TomlValue* body = nullptr;
-            if (const TomlValue* cv = cfg.find("camera_velocity")) enum_variant(*cv, "camera_velocity", mode, body);
-            if (mode == "StaticObserver") vel = geo.stationary_velocity(pos);
-            else if (mode == "Zamo") vel = geo.zamo_velocity(pos);
-            else if (mode == "Explicit") {
+            if (const TomlValue* cv = cfg.find("camera_velocity")) enum_variant(*cv, "camera_velocity", hs.camera_velocity_mode, body);
+            if (hs.camera_velocity_mode == "Explicit") {
                 const TomlValue& comps = need(*body, "components", "Explicit");
                 if (comps.kind != TomlValue::ARRAY || comps.arr.size() != 4) bad(GRRT_ERR_TOML, "Explicit.components needs 4 numbers");
-                for (int i = 0; i < 4; ++i) vel[i] = comps.arr[i].as_double();
-                double n = geo.inner(pos, vel, vel);
-                if (std::fabs(n - geo.sig0()) > 1e-6) bad(GRRT_ERR_INVALID_CONFIGURATION, "Explicit camera_velocity is not normalized");
-            } else {
-                bad(GRRT_ERR_TOML, "unknown variant `" + mode + "` for camera_velocity");
+                for (int i = 0; i < 4; ++i) hs.camera_velocity_explicit[i] = comps.arr[i].as_double();
             }
-            Vec4 tt = geo.tetrad_at(pos).t;
-            double orientation = geo.sig0() * geo.inner(pos, tt, vel);
-            if (!(std::isfinite(vel[0]) && 1.0 * orientation > 0.0))
-                bad(GRRT_ERR_INVALID_CONFIGURATION, "camera four-velocity has wrong time orientation");
         }
+        Vec4 vel = resolve_camera_velocity(geo, pos, hs.camera_velocity_mode, hs.camera_velocity_explicit);
 
         // create_scene (cli/shared.rs:131-321)
         const TomlValue* adc = cfg.find("adaptive_sampling");
@@ -858,32 +893,7 @@ struct SceneBuilder {
         sc.kerr_rhs_mode = GRRT_KERR_RHS_REFERENCE_FD;
         sc.celestial = texture(need(cfg, "celestial_texture", "RenderConfig"));
 
-        // Camera::new (camera.rs:151-196): alpha = PI/4, rows = height, cols = width
-        {
-            Frame T0 = geo.tetrad_at(pos);
-            if (!geo.orthonormal(pos, T0)) bad(GRRT_ERR_TETRAD_NOT_ORTHONORMAL, "Tetrad is not orthonormal");
-            Vec4 a1, b1, z, a2, x, y;
-            rotate_pair(T0.x, T0.y, opts.phi, a1, b1);
-            rotate_pair(T0.z, a1, opts.theta, z, a2);
-            rotate_pair(a2, b1, opts.psi, x, y);
-            Mat4 L = geo.lorentz(pos, vel);
-            Frame T{matvec(L, T0.t), matvec(L, x), matvec(L, y), matvec(L, z)};
-            if (!geo.orthonormal(pos, T)) bad(GRRT_ERR_TETRAD_NOT_ORTHONORMAL, "Tetrad is not orthonormal");
-            GrrtCamera& cam = sc.camera;
-            for (int i = 0; i < 4; ++i) {
-                cam.position[i] = pos[i];
-                cam.velocity[i] = vel[i];
-                cam.tetrad[0][i] = T.t[i];
-                cam.tetrad[1][i] = T.x[i];
-                cam.tetrad[2][i] = T.y[i];
-                cam.tetrad[3][i] = T.z[i];
-            }
-            cam.alpha = PI / 4.0;
-            cam.rows = opts.height;
-            cam.cols = opts.width;
-            cam.spatial_signature = -geo.sig0();
-            cam.spatial_handedness = geo.handedness(pos, T);
-        }
+        make_camera(geo, pos, vel, opts, sc.camera);
 
         // objects
         if (const TomlValue* objs = cfg.find("objects")) {
@@ -1025,6 +1035,28 @@ int build_scene_from_toml(const std::string& text, const char* resource_root, co
     } catch (const TomlError& e) {
         err = e.what();
         return GRRT_ERR_TOML;
+    } catch (const ConfigError& e) {
+        err = e.msg;
+        return e.code;
+    } catch (const std::exception& e) {
+        err = e.what();
+        return GRRT_ERR_INVALID_ARGUMENT;
+    }
+}
+
+// A new camera for an assembled scene (animation frames): position, angles and frame size from `opts`, everything
+// else -- textures, look-up tables, objects, integration limits -- stays as built.
+int update_camera(HostSceneData& hsd, const GrrtCliOpts& opts, std::string& err) {
+    try {
+        if (opts.width <= 0 || opts.height <= 0) bad(GRRT_ERR_INVALID_CONFIGURATION, "--width and --height must be positive");
+        HostGeometry geo(hsd.scene.geometry);
+        Vec4 pos = geo.camera_position_native(opts.camera_position);
+        Vec4 vel = resolve_camera_velocity(geo, pos, hsd.camera_velocity_mode, hsd.camera_velocity_explicit);
+        GrrtCamera cam;
+        std::memset(&cam, 0, sizeof cam);
+        make_camera(geo, pos, vel, opts, cam);
+        hsd.scene.camera = cam;
+        return GRRT_OK;
     } catch (const ConfigError& e) {
         err = e.msg;
         return e.code;

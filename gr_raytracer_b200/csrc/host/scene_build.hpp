@@ -28,10 +28,13 @@ struct HostSceneData {
     std::vector<HostBitmap> bitmaps;
     std::list<HostTempLut> temp_luts;
     std::vector<double> bb_log_t, bb_xyz;
+    std::string camera_velocity_mode = "StaticObserver";  // [camera_velocity] of the scene file, kept for update_camera()
+    double camera_velocity_explicit[4] = {0.0, 0.0, 0.0, 0.0};
 };
 
 int build_scene_from_toml(const std::string& text, const char* resource_root, const GrrtCliOpts& opts, HostSceneData& out,
                           std::string& err);
+int update_camera(HostSceneData& scene, const GrrtCliOpts& opts, std::string& err);
 int ray_at(const GrrtGeometry& g, const double position_cartesian[3], const double direction[3], double pos_out[4],
            double mom_out[4], std::string& err);
 void step_to_cartesian(const GrrtGeometry& g, const double x[4], double out[4]);

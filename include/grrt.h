@@ -275,6 +275,17 @@ int grrt_trace_pixel_ray(GrrtCtx* ctx, const GrrtScene* scene, int64_t row, int6
 int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* scene, GrrtDeviceScene** out);
 void grrt_scene_free(GrrtCtx* ctx, GrrtDeviceScene* dscene);
 
+/* Animation frames (the reference re-runs its binary per camera position,
+ * scripts/Readme.md "Camera fly-through movie"): keep textures and look-up tables
+ * resident, replace only the camera (Camera::new output, camera.rs:16-25), and render
+ * the resident scene into HOST buffers exactly as grrt_render does.  The frame equals
+ * grrt_render of a scene assembled with that camera, bit for bit. */
+int grrt_scene_set_camera(GrrtCtx* ctx, GrrtDeviceScene* dscene, const GrrtCamera* camera);
+int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* dscene,
+                         uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
+                         double* xyza_out, uint8_t* ray_class_out, uint8_t* stop_reason_out,
+                         uint32_t* steps_out, GrrtStats* stats);
+
 /* Trace `n_items` work items.  Item i is pixel id items[i] of the rectangle
  * [from_row,to_row) x [from_col,to_col), numbered row-major from its top-left corner
  * (items == NULL: the consecutive ids first_item .. first_item+n_items-1).  samples_per_axis == 0:
@@ -341,6 +352,9 @@ int grrt_host_scene_from_toml_string(const char* toml_text, const char* resource
                                      char* err, size_t err_len);
 const GrrtScene* grrt_host_scene_get(const GrrtHostScene* hs);
 void grrt_host_scene_free(GrrtHostScene* hs);
+/* Recomputes only the camera of an assembled scene (position, phi/theta/psi, width and
+ * height of `opts`; cli/shared.rs:23-86 + Camera::new): one call per animation frame. */
+int grrt_host_scene_set_camera(GrrtHostScene* hs, const GrrtCliOpts* opts, char* err, size_t err_len);
 /* render-ray-at: momentum from a Cartesian direction in the unboosted tetrad
  * (cli/schwarzschild.rs:89-121, cli/kerr.rs:77-100, cli/kerr_bl.rs:78-107). */
 int grrt_host_ray_at(const GrrtGeometry* geometry, const double position_cartesian[3],

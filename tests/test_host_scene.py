@@ -242,3 +242,23 @@ def test_hdr_writer(tmp_path):
     r, g, b, e = (int(v) for v in px[1, 1])
     scale = 2.0 ** (e - 128) / 256.0
     assert abs(r * scale - 0.5) <= scale and abs(g * scale - 1.25) <= scale and abs(b * scale - 300.0) <= scale
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3"])
+def test_camera_update_equals_fresh_assembly(name):
+    """grrt_host_scene_set_camera (animation frames): recomputing only the camera of an assembled scene gives the
+    bytes of a scene assembled from scratch with those options, and a failed update keeps the previous camera."""
+    toml = os.path.join(ROOT, CONFIGS[name]["toml"])
+    kw = dict(camera_position=(-9.0, 2.0, 0.4), phi=0.05, theta=-3.1, psi=0.02)
+    sc = api.HostScene(toml, config_opts(name, width=16, height=12), ROOT)
+    sc.set_camera(**kw)
+    fresh = api.HostScene(toml, config_opts(name, width=16, height=12, **kw), ROOT)
+    assert bytes(sc.c.camera) == bytes(fresh.c.camera)
+    assert sc.c.n_objects == fresh.c.n_objects and sc.c.integration.max_steps == fresh.c.integration.max_steps
+    if name != "C3":   # Kerr-Schild coordinates have a static observer only outside the ergosphere; r = 0.3 r_s has none
+        before = bytes(sc.c.camera)
+        with pytest.raises(api.GrrtError):
+            sc.set_camera(camera_position=(0.3, 0.0, 0.0))
+        assert bytes(sc.c.camera) == before
+    sc.close()
+    fresh.close()
