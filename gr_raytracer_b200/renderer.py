@@ -117,6 +117,8 @@ class FrameRenderer:
             self.gat_xyza = engine.new((world, m, 4), torch.float64)
             self.gat_meta = engine.new((world, m, 2), torch.uint8)
         self.last = {}
+        self.profile = False   # True: CUDA-event timestamps of the phases of render() in self.phase_ms (adds syncs)
+        self.phase_ms = {}
 
     def _all_gather(self, out, inp):
         import torch.distributed as dist
@@ -125,10 +127,20 @@ class FrameRenderer:
     def render(self):
         """Renders the frame into self.xyza / cls / stop / steps (device).  Returns ray counts."""
         e, ad = self.e, self.ad
+        marks = []
+
+        def mark(name):
+            if self.profile:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         if self.world == 1:
             e.trace(None, self.n, self.rect, 0, self.xyza, self.cls, self.stop, self.steps)
         else:
             e.trace(self.my_items, self.n_mine, self.rect, 0, self.loc_xyza, self.loc_cls, self.loc_stop, self.loc_steps)
+            mark("base")
             meta = torch.stack((self.loc_cls, self.loc_stop), dim=1)
             self._all_gather(self.gat_xyza.view(-1, 4), self.loc_xyza)
             self._all_gather(self.gat_meta.view(-1, 2), meta)
@@ -136,11 +148,13 @@ class FrameRenderer:
             meta_all = self.gat_meta.view(-1, 2).index_select(0, self.gather_src)
             self.cls.index_copy_(0, self.gather_dst, meta_all[:, 0].contiguous())
             self.stop.index_copy_(0, self.gather_dst, meta_all[:, 1].contiguous())
+        mark("gather_base")
         n_sel = 0
         min_lum = 0.0
         if ad.enabled or ad.show_sampling_mask:
             min_lum = e.select(self.xyza, self.cls, self.H, self.W, self.selected, self.count)
             n_sel = int(self.count.item())
+            mark("mask")
             if n_sel and ad.show_sampling_mask:
                 col = torch.tensor(list(ad.mask_xyza), dtype=torch.float64, device=self.xyza.device)
                 self.xyza[self.selected[:n_sel].long()] = col
@@ -158,11 +172,16 @@ class FrameRenderer:
                     if k:
                         e.trace(mine, k, self.rect, spa, scratch)
                         loc[:k] = scratch[mine.long()]
+                    mark("supersample")
                     gat = self.e.new((self.world, per, 4), torch.float64)
                     self._all_gather(gat.view(-1, 4), loc)
                     for r in range(self.world):
                         ids = self.selected[:n_sel][r::self.world].long()
                         self.xyza.index_copy_(0, ids, gat[r, :ids.numel()])
+        mark("end")
+        if self.profile:
+            torch.cuda.synchronize()
+            self.phase_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
         ss = int(ad.samples_per_axis) ** 2 if (n_sel and not ad.show_sampling_mask) else 0
         self.last = dict(rays_base=self.n, pixels_supersampled=n_sel, rays_supersample=n_sel * ss,
                          minimum_luminance=min_lum)
