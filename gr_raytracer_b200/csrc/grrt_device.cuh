@@ -60,9 +60,11 @@ __constant__ double c_trig[16] = {
     4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,    // 9..14: C1..C6
     -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,
     0.0};
+// large or non-finite arguments: the library's Payne-Hanek path, out of line (never taken by a healthy geodesic)
+__device__ __noinline__ void sincos_large(double x, double* sn, double* cs) { sincos(x, sn, cs); }
 GD void sincos_pi2(double x, double* sn, double* cs) {
     if (!(fabs(x) < 1.0e5)) {
-        sincos(x, sn, cs);
+        sincos_large(x, sn, cs);
         return;
     }
     const double kd = rint(x * c_trig[0]);

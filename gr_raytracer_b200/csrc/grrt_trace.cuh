@@ -343,6 +343,12 @@ __device__ __forceinline__ Cie vol_march_warp(const DScene& S, const DObject& o,
 // ---- the kernel ----------------------------------------------------------------------------------------
 enum { ST_IDLE = 0, ST_ACTIVE = 1, ST_DEAD = 2 };
 
+#ifdef GRRT_FAST_MATH
+// The step-size controller's exact path is cold in the fast build (seed out of range, err = 0 / inf / NaN): kept out
+// of line so that the attempt loop stays short.
+__device__ __noinline__ double controller_pow_cold(double x) { return pow_glibc(pow_tables_global(), x, 1.0 / 5.0); }
+#endif
+
 // the exact build keeps the glibc-compatible pow tables in shared memory (one pow per attempt); the fast build only
 // needs them on the controller's rare fallback path and reads them from global memory
 #ifdef GRRT_FAST_MATH
@@ -367,10 +373,8 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
     unsigned char* s_tail = reinterpret_cast<unsigned char*>(s_ctx + (HAS_VOL ? CX_SLOTS_VOL : CX_SLOTS) * kTraceThreads);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+#ifndef GRRT_FAST_MATH
     PowTables pow_tab;
-#ifdef GRRT_FAST_MATH
-    pow_tab = pow_tables_global();
-#else
     double (*s_pow_log)[3] = reinterpret_cast<double (*)[3]>(s_tail);        // glibc-compatible pow tables
     unsigned long long* s_pow_exp = reinterpret_cast<unsigned long long*>(s_pow_log + 128);
     for (int i = tid; i < 128 * 3; i += kTraceThreads) (&s_pow_log[0][0])[i] = (&kPowLogTab[0][0])[i];
@@ -545,7 +549,11 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                     h_proposed = 0.9 * h_cur * z;
                 } else
 #endif
+#ifdef GRRT_FAST_MATH
+                if (err > 0.0) h_proposed = 0.9 * h_cur * controller_pow_cold(S.epsilon / err);
+#else
                 if (err > 0.0) h_proposed = 0.9 * h_cur * pow_glibc(pow_tab, S.epsilon / err, 1.0 / 5.0);
+#endif
                 else h_proposed = h_cur * kHGrowthCap;
                 h_proposed = rclamp(fmin(h_proposed, h_cur * kHGrowthCap), kHMin, kHMax);
                 if (err > S.epsilon) {
@@ -595,7 +603,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                             bool hit;
                             if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
                             else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
-                            else hit = vol_intersects(o, prev_cart, cart, hcur);
+                            else hit = HAS_VOL ? vol_intersects(o, prev_cart, cart, hcur) : false;  // no such object without HAS_VOL
                             if (!hit) continue;
                             const double distance = norm3(hcur.point - prev_cart);
                             if (!(distance < shortest)) continue;
@@ -651,7 +659,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 bool hit;
                 if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
                 else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
-                else hit = vol_intersects(o, prev_cart, cart, hcur);
+                else hit = HAS_VOL ? vol_intersects(o, prev_cart, cart, hcur) : false;  // no such object without HAS_VOL
                 if (!hit) continue;
                 // step_at_intersection (objects.rs:27-44): exact point, lerped momentum
                 double p0[4], p1[4], xs[4], ps[4];
