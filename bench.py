@@ -365,8 +365,8 @@ def main():
                     "traffic": None}
         if args.workload == "C2" and (W, H) == (1500, 1500) and world == 1:
             # dram__bytes_read.sum + dram__bytes_write.sum of the base-pass launch, ncu --set full capture of this command
-            roofline["traffic"] = 23.763712e6 + 51.967232e6
-            roofline["traffic_source"] = "profiles/r1_c2_trace_kernel_v6_1500.json (bytes per base-pass launch; the frame buffers, no re-reads)"
+            roofline["traffic"] = 26.936320e6 + 75.075840e6
+            roofline["traffic_source"] = "profiles/r1_c2_trace_kernel_v12_1500.json (bytes per base-pass launch: the 85.5 MB of frame buffers written once, scene tables read once)"
         if kern_ms:
             ach = kern_flops / (kern_ms * 1e-3) / 1e12
             roofline.update({"achieved": ach, "frac": ach / peak_tflops, "kernel": "trace_kernel", "kernel_ms_per_launch": kern_ms,
