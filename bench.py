@@ -398,6 +398,7 @@ def main():
                                 "sample": res["sample"], "rkf45_steps_per_s": res["steps"] / res["seconds"], "seconds": res["seconds"]}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    fr.close()
     engine.close()
     if world > 1:
         dist.destroy_process_group()

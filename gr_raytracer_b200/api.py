@@ -59,6 +59,12 @@ def lib():
                                        C.POINTER(abi.GrrtStats)]
     L.grrt_trace_items_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp]
+    L.grrt_trace_items_device_peers.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, vp]
+    L.grrt_ipc_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    L.grrt_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.grrt_ipc_close.argtypes = [vp, vp]
+    L.grrt_ipc_free.argtypes = [vp, vp]
     L.grrt_select_mask_device.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, dp, vp]
     L.grrt_tonemap_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_double, vp, vp]
     L.grrt_measure_fp64_peak.argtypes = [vp, dp, dp]
@@ -291,6 +297,33 @@ class Context:
         fr, fc, tr, tc = rect
         return self._check(lib().grrt_trace_items_device(self._h, dscene, d_items, first_item, n_items, fr, fc, tr, tc,
                                                          spa, d_xyza, d_class, d_stop, d_steps, d_counters, stream))
+
+    def trace_items_device_peers(self, dscene, d_items, n_items, rect, spa, xyza_peers, class_peers, stop_peers,
+                                 d_counters=None, stream=None):
+        """grrt_trace_items_device_peers: results go at their pixel id into every peer's frame buffers."""
+        fr, fc, tr, tc = rect
+        n = len(xyza_peers)
+        arr = lambda ptrs: (C.c_void_p * n)(*[int(p) for p in ptrs])
+        return self._check(lib().grrt_trace_items_device_peers(self._h, dscene, d_items, n_items, fr, fc, tr, tc, spa, n,
+                                                               arr(xyza_peers), arr(class_peers), arr(stop_peers),
+                                                               d_counters, stream))
+
+    # -- frame buffers shared between the processes of one box (cudaIpc) ------------------------------
+    def ipc_alloc(self, nbytes):
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        self._check(lib().grrt_ipc_alloc(self._h, nbytes, C.byref(ptr), handle))
+        return ptr.value, handle.raw
+
+    def ipc_open(self, handle):
+        ptr = C.c_void_p()
+        self._check(lib().grrt_ipc_open(self._h, handle, C.byref(ptr)))
+        return ptr.value
+
+    def ipc_close(self, ptr):
+        self._check(lib().grrt_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def ipc_free(self, ptr):
+        self._check(lib().grrt_ipc_free(self._h, C.c_void_p(ptr)))
 
     def select_mask_device(self, dscene, d_xyza, d_class, rows, cols, d_selected, d_count, stream=None):
         ml = C.c_double()

@@ -231,8 +231,12 @@ __global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, int iters,
 }
 
 // mean over the valid sub-samples, summed in stratum order (raytracer.rs:341-379)
+struct PeerFrames {
+    unsigned n;
+    double* xyza[GRRT_MAX_PEERS];
+};
 __global__ void grrt_exact_resolve(const double* sub_xyza, const uint8_t* sub_valid, const uint32_t* items,
-                                   unsigned long long n_items, unsigned ss, double* xyza) {
+                                   unsigned long long n_items, unsigned ss, double* xyza, PeerFrames peers) {
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     double sx = 0.0, sy = 0.0, sz = 0.0, sa = 0.0;
@@ -247,8 +251,16 @@ __global__ void grrt_exact_resolve(const double* sub_xyza, const uint8_t* sub_va
     }
     if (valid > 0) {
         double inv = 1.0 / (double)valid;
-        double* dst = xyza + 4ull * items[i];
-        dst[0] = sx * inv; dst[1] = sy * inv; dst[2] = sz * inv; dst[3] = sa * inv;
+        const double m0 = sx * inv, m1 = sy * inv, m2 = sz * inv, m3 = sa * inv;
+        if (peers.n == 0) {
+            double* dst = xyza + 4ull * items[i];
+            dst[0] = m0; dst[1] = m1; dst[2] = m2; dst[3] = m3;
+        } else {
+            for (unsigned p = 0; p < peers.n; ++p) {  // the mean goes into every rank's frame
+                double* dst = peers.xyza[p] + 4ull * items[i];
+                dst[0] = m0; dst[1] = m1; dst[2] = m2; dst[3] = m3;
+            }
+        }
     }
 }
 
@@ -485,11 +497,12 @@ void grrt_scene_free(GrrtCtx* ctx, GrrtDeviceScene* ds) {
     delete ds;
 }
 
-int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_items, uint64_t first_item,
-                            uint64_t n_items, uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
-                            uint32_t samples_per_axis, double* d_xyza, uint8_t* d_class, uint8_t* d_stop,
-                            uint32_t* d_steps, uint64_t* d_counters, void* cuda_stream) {
-    if (!ctx || !ds || !d_xyza) return GRRT_ERR_INVALID_ARGUMENT;
+namespace {
+int trace_items_impl(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_items, uint64_t first_item,
+                     uint64_t n_items, uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
+                     uint32_t samples_per_axis, double* d_xyza, uint8_t* d_class, uint8_t* d_stop, uint32_t* d_steps,
+                     uint64_t* d_counters, void* cuda_stream, uint32_t n_peers, double* const* xyza_peers,
+                     uint8_t* const* class_peers, uint8_t* const* stop_peers) {
     if (to_row < from_row || to_col < from_col) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "empty or inverted section");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
@@ -505,6 +518,10 @@ int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint3
     a.height = to_row - from_row;
     a.queue = ctx->d_queue;
     a.counters = (unsigned long long*)d_counters;
+    PeerFrames pf;
+    std::memset(&pf, 0, sizeof pf);
+    pf.n = n_peers;
+    for (uint32_t p = 0; p < n_peers; ++p) pf.xyza[p] = xyza_peers[p];
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned long long), st));
     if (samples_per_axis == 0) {
         a.spa = 0;
@@ -512,6 +529,12 @@ int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint3
         a.cls = d_class;
         a.stop = d_stop;
         a.steps = d_steps;
+        a.n_peers = n_peers;
+        for (uint32_t p = 0; p < n_peers; ++p) {
+            a.xyza_p[p] = xyza_peers[p];
+            a.cls_p[p] = class_peers[p];
+            a.stop_p[p] = stop_peers[p];
+        }
         const bool whole = !d_items && first_item == 0 && n_items == (uint64_t)a.width * a.height;
         if (whole) {  // enumerate 8x4 pixel tiles so that a warp starts on a compact patch of the image
             a.tiled = 1;
@@ -542,11 +565,72 @@ int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint3
         int rc = launch_trace(ctx, ds, a, st);
         if (rc) return rc;
         grrt_exact_resolve<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(sub.as<double>(), valid.as<uint8_t>(),
-                                                                                d_items + off, m, ss, d_xyza);
+                                                                                d_items + off, m, ss, d_xyza, pf);
         ++ctx->launches;
         CUDA_TRY(ctx, cudaGetLastError());
     }
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));  // scratch is freed on return
+    return GRRT_OK;  // the scratch buffers are freed in stream order
+}
+}  // namespace
+
+int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_items, uint64_t first_item,
+                            uint64_t n_items, uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
+                            uint32_t samples_per_axis, double* d_xyza, uint8_t* d_class, uint8_t* d_stop,
+                            uint32_t* d_steps, uint64_t* d_counters, void* cuda_stream) {
+    if (!ctx || !ds || !d_xyza) return GRRT_ERR_INVALID_ARGUMENT;
+    return trace_items_impl(ctx, ds, d_items, first_item, n_items, from_row, from_col, to_row, to_col, samples_per_axis, d_xyza,
+                            d_class, d_stop, d_steps, d_counters, cuda_stream, 0, nullptr, nullptr, nullptr);
+}
+
+int grrt_trace_items_device_peers(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_items, uint64_t n_items,
+                                  uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
+                                  uint32_t samples_per_axis, uint32_t n_peers, double* const* d_xyza_peers,
+                                  uint8_t* const* d_class_peers, uint8_t* const* d_stop_peers, uint64_t* d_counters,
+                                  void* cuda_stream) {
+    if (!ctx || !ds || !d_items || !d_xyza_peers || !d_class_peers || !d_stop_peers) return GRRT_ERR_INVALID_ARGUMENT;
+    if (n_peers == 0 || n_peers > GRRT_MAX_PEERS) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "1..GRRT_MAX_PEERS peers");
+    for (uint32_t p = 0; p < n_peers; ++p)
+        if (!d_xyza_peers[p] || !d_class_peers[p] || !d_stop_peers[p]) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "null peer buffer");
+    return trace_items_impl(ctx, ds, d_items, 0, n_items, from_row, from_col, to_row, to_col, samples_per_axis, d_xyza_peers[0],
+                            nullptr, nullptr, nullptr, d_counters, cuda_stream, n_peers, d_xyza_peers, d_class_peers,
+                            d_stop_peers);
+}
+
+// ---- frame buffers shared between the processes of one box (cudaIpc) -----------------------------------------
+int grrt_ipc_alloc(GrrtCtx* ctx, size_t bytes, void** d_ptr, unsigned char handle_out[64]) {
+    if (!ctx || !d_ptr || !handle_out) return GRRT_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&p, bytes ? bytes : 1));   // plain cudaMalloc: pool allocations cannot be exported
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        CUDA_TRY(ctx, e);
+    }
+    std::memcpy(handle_out, &h, 64);
+    *d_ptr = p;
+    return GRRT_OK;
+}
+int grrt_ipc_open(GrrtCtx* ctx, const unsigned char handle[64], void** d_ptr) {
+    if (!ctx || !handle || !d_ptr) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CUDA_TRY(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GRRT_OK;
+}
+int grrt_ipc_close(GrrtCtx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return GRRT_OK;
+}
+int grrt_ipc_free(GrrtCtx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaFree(d_ptr));
     return GRRT_OK;
 }
 

@@ -455,7 +455,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                         CTX(CX_PREV_X) = c0.x;
                         CTX(CX_PREV_Y) = c0.y;
                         CTX(CX_PREV_Z) = c0.z;
-                        R.unit = A.tiled ? item : unit;
+                        R.unit = (A.tiled || A.n_peers) ? pid : unit;  // index of the ray's result in the output buffers
                         R.step = 0;
                         R.attempts = 0;
                         R.n_hits = 0;
@@ -781,7 +781,17 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
             }
             // write out
             const unsigned long long o = R.unit;
-            if (A.spa == 0) {
+            if (A.spa == 0 && A.n_peers) {
+                // multi-GPU frame: the finished pixel goes straight into every rank's frame over NVLink (33 B per
+                // peer per ray), so no gather / scatter pass follows the kernel
+                for (unsigned p = 0; p < A.n_peers; ++p) {
+                    double* dst = A.xyza_p[p] + 4 * o;
+                    dst[0] = result.x; dst[1] = result.y; dst[2] = result.z; dst[3] = result.a;
+                    A.cls_p[p][o] = (uint8_t)ray_class;
+                    A.stop_p[p][o] = (uint8_t)finish;
+                }
+                if (A.steps) A.steps[o] = (uint32_t)R.step;
+            } else if (A.spa == 0) {
                 double* dst = A.xyza + 4 * o;
                 dst[0] = result.x; dst[1] = result.y; dst[2] = result.z; dst[3] = result.a;
                 if (A.cls) A.cls[o] = (uint8_t)ray_class;

@@ -86,6 +86,12 @@ struct TraceArgs {
     uint8_t* sub_valid;          // spa > 0: per unit
     unsigned long long* queue;
     unsigned long long* counters;
+    // n_peers > 0 (spa == 0 only): results are written at the item's PIXEL id into every peer's frame buffers
+    // (peer-mapped device pointers, this GPU's own included) instead of compactly into xyza / cls / stop
+    uint32_t n_peers;
+    double* xyza_p[GRRT_MAX_PEERS];
+    uint8_t* cls_p[GRRT_MAX_PEERS];
+    uint8_t* stop_p[GRRT_MAX_PEERS];
 };
 
 

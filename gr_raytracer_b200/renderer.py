@@ -6,14 +6,18 @@ Multi-GPU (BASELINE.json north_star): pixels are independent, so the image is cu
 tiles dealt round-robin to the ranks (fine-grained interleaving balances the spatially clustered
 shadow / disc work without a pilot pass).  The only coupling is the adaptive mask: it reads the 8
 neighbours of every pixel and a frame-global 99th-percentile luminance (raytracer.rs:118-129,
-386-458), so the 1-spp base buffer (33 B per pixel) is exchanged once with an all-gather; every rank
-then derives the same mask, supersamples its share of the flagged pixels and the per-pixel means are
-all-gathered.  No reduction is involved; the N-GPU image is bit-identical to the 1-GPU image.
+386-458), so every rank needs the whole 1-spp base buffer (33 B per pixel); every rank then derives the
+same mask and supersamples its share of the flagged pixels.  No reduction is involved; the N-GPU image is
+bit-identical to the 1-GPU image.  The exchange is fused into the kernels: the ranks map each other's frame
+buffers (cudaIpc, NVLink peer access) and the trace kernel / the sub-sample mean kernel store every finished
+pixel into all of them, with a one-word all-reduce as the barrier between passes.  Where the buffers cannot be
+shared (or with GRRT_P2P=0) the same frame is assembled with NCCL all-gathers.
 
 torch is plumbing here (device buffers, the current stream, the collective); the ray tracing, mask
 selection and tone mapping are the CUDA kernels of libgrrt.so reached through the C ABI.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -82,6 +86,35 @@ class DeviceEngine:
     def new(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    # -- frame buffers mapped into every rank of the box (cudaIpc), for the gather-free multi-GPU path ----------
+    supports_peers = True
+
+    def shared_alloc(self, nbytes):
+        return self.ctx.ipc_alloc(nbytes)          # (device pointer, 64-byte handle)
+
+    def shared_open(self, handle):
+        return self.ctx.ipc_open(handle)
+
+    def shared_close(self, ptr):
+        self.ctx.ipc_close(ptr)
+
+    def shared_free(self, ptr):
+        self.ctx.ipc_free(ptr)
+
+    def wrap(self, ptr, shape, dtype):
+        """A torch view of raw device memory (not owned by torch)."""
+        typestr = {torch.float64: "<f8", torch.uint8: "|u1"}[dtype]
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+        return torch.as_tensor(raw, device=self.device)
+
+    def trace_peers(self, items, n_items, rect, spa, xyza_ptrs, cls_ptrs, stop_ptrs):
+        self.ctx.trace_items_device_peers(self.dscene, self._p(items), n_items, rect, spa, xyza_ptrs, cls_ptrs, stop_ptrs,
+                                          self._p(self.counters), self._stream())
+
 
 class FrameRenderer:
     """One frame = base pass + mask + supersampling, sharded over `world` ranks."""
@@ -93,9 +126,14 @@ class FrameRenderer:
         n = self.W * self.H
         self.n = n
         self.rect = (0, 0, self.H, self.W)
-        self.xyza = engine.new((n, 4), torch.float64)
-        self.cls = engine.new((n,), torch.uint8)
-        self.stop = engine.new((n,), torch.uint8)
+        self.p2p = False
+        self._own, self._opened = [], []
+        if world > 1 and getattr(engine, "supports_peers", False) and os.environ.get("GRRT_P2P", "1") != "0":
+            self._setup_peer_frames()
+        if not self.p2p:
+            self.xyza = engine.new((n, 4), torch.float64)
+            self.cls = engine.new((n,), torch.uint8)
+            self.stop = engine.new((n,), torch.uint8)
         self.steps = engine.new((n,), torch.int32)
         self.selected = engine.new((n,), torch.int32)
         self.count = engine.new((1,), torch.int32)
@@ -110,6 +148,7 @@ class FrameRenderer:
             self.gather_src = torch.from_numpy(src).to(self.xyza.device)
             self.gather_dst = torch.from_numpy(np.concatenate(per_rank)).to(self.xyza.device)
             m = self.max_items
+        if world > 1 and not self.p2p:
             self.loc_xyza = engine.new((m, 4), torch.float64)
             self.loc_cls = engine.new((m,), torch.uint8)
             self.loc_stop = engine.new((m,), torch.uint8)
@@ -119,6 +158,71 @@ class FrameRenderer:
         self.last = {}
         self.profile = False   # True: CUDA-event timestamps of the phases of render() in self.phase_ms (adds syncs)
         self.phase_ms = {}
+
+    def _setup_peer_frames(self):
+        """Frame buffers of every rank mapped into every rank (cudaIpc over NVLink): the trace kernel stores each
+        finished pixel into all of them, so no gather / scatter pass is needed.  Falls back (on every rank) to the
+        all-gather path if any rank cannot export or map the buffers."""
+        import torch.distributed as dist
+        e, n, world = self.e, self.n, self.world
+        ok = 1
+        sizes = (n * 32, n, n)
+        try:
+            own = [e.shared_alloc(sz) for sz in sizes]
+        except Exception:
+            own, ok = [], 0
+        self._own = [p for p, _ in own]
+        blob = b"".join(h for _, h in own) if ok else bytes(192)
+        mine = torch.tensor(list(blob), dtype=torch.uint8, device=e.device)
+        allh = torch.empty((world, 192), dtype=torch.uint8, device=e.device)
+        dist.all_gather_into_tensor(allh.view(-1), mine, group=self.group)
+        flag = torch.tensor([ok], dtype=torch.int32, device=e.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        peers = [[None] * world for _ in range(3)]
+        if int(flag.item()):
+            allh = allh.cpu().numpy()
+            try:
+                for r in range(world):
+                    for b in range(3):
+                        if r == self.rank:
+                            peers[b][r] = self._own[b]
+                        else:
+                            ptr = e.shared_open(bytes(allh[r, 64 * b:64 * (b + 1)]))
+                            self._opened.append(ptr)
+                            peers[b][r] = ptr
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=e.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if not int(flag.item()):
+            self.close()
+            return
+        self.peer_xyza, self.peer_cls, self.peer_stop = peers
+        self.xyza = e.wrap(self._own[0], (n, 4), torch.float64)
+        self.cls = e.wrap(self._own[1], (n,), torch.uint8)
+        self.stop = e.wrap(self._own[2], (n,), torch.uint8)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=e.device)
+        self.p2p = True
+
+    def close(self):
+        """Unmaps / frees the shared frame buffers (the tensors xyza / cls / stop must not be used afterwards)."""
+        if self.p2p or self._own or self._opened:
+            torch.cuda.synchronize()
+            if self.world > 1 and self.p2p:
+                import torch.distributed as dist
+                dist.barrier(group=self.group)   # nobody unmaps while a peer may still store into the buffers
+            for ptr in self._opened:
+                self.e.shared_close(ptr)
+            for ptr in self._own:
+                self.e.shared_free(ptr)
+            self._opened, self._own, self.p2p = [], [], False
+
+    def _barrier(self):
+        """Orders the passes across ranks on the current stream: completes once every rank's earlier work has."""
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)
 
     def _all_gather(self, out, inp):
         import torch.distributed as dist
@@ -138,6 +242,10 @@ class FrameRenderer:
         mark("start")
         if self.world == 1:
             e.trace(None, self.n, self.rect, 0, self.xyza, self.cls, self.stop, self.steps)
+        elif self.p2p:
+            e.trace_peers(self.my_items, self.n_mine, self.rect, 0, self.peer_xyza, self.peer_cls, self.peer_stop)
+            mark("base")
+            self._barrier()
         else:
             e.trace(self.my_items, self.n_mine, self.rect, 0, self.loc_xyza, self.loc_cls, self.loc_stop, self.loc_steps)
             mark("base")
@@ -155,6 +263,8 @@ class FrameRenderer:
             min_lum = e.select(self.xyza, self.cls, self.H, self.W, self.selected, self.count)
             n_sel = int(self.count.item())
             mark("mask")
+            if self.p2p:
+                self._barrier()   # no rank may store sub-sample means into a frame whose mask is still being computed
             if n_sel and ad.show_sampling_mask:
                 col = torch.tensor(list(ad.mask_xyza), dtype=torch.float64, device=self.xyza.device)
                 self.xyza[self.selected[:n_sel].long()] = col
@@ -162,6 +272,12 @@ class FrameRenderer:
                 spa = int(ad.samples_per_axis)
                 if self.world == 1:
                     e.trace(self.selected, n_sel, self.rect, spa, self.xyza)
+                elif self.p2p:
+                    mine = self.selected[:n_sel][self.rank::self.world].contiguous()
+                    if int(mine.numel()):
+                        e.trace_peers(mine, int(mine.numel()), self.rect, spa, self.peer_xyza, self.peer_cls, self.peer_stop)
+                    mark("supersample")
+                    self._barrier()
                 else:
                     # flagged pixels dealt round-robin; every rank writes its means into a frame-sized scratch
                     mine = self.selected[:n_sel][self.rank::self.world].contiguous()

@@ -300,6 +300,25 @@ int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* dscene,
                             uint32_t* d_steps, uint64_t* d_counters /* 16 u64, accumulated */,
                             void* cuda_stream);
 
+/* Multi-GPU frames without a gather pass (tiles travel by peer stores, there
+ * is no reduction).  Every rank allocates its frame buffers with grrt_ipc_alloc, the 64-byte
+ * handles are exchanged by the host (e.g. torch.distributed), grrt_ipc_open maps the peers'
+ * buffers, and grrt_trace_items_device_peers writes each finished pixel at its PIXEL id into
+ * all `n_peers` frames (own pointer included) straight from the trace kernel / the sub-sample
+ * mean kernel.  The pointer arrays are HOST arrays of device pointers.  The caller orders the
+ * passes across ranks (a barrier after each call) before reading its frame. */
+#define GRRT_MAX_PEERS 8
+int grrt_ipc_alloc(GrrtCtx* ctx, size_t bytes, void** d_ptr, unsigned char handle_out[64]);
+int grrt_ipc_open(GrrtCtx* ctx, const unsigned char handle[64], void** d_ptr);
+int grrt_ipc_close(GrrtCtx* ctx, void* d_ptr);
+int grrt_ipc_free(GrrtCtx* ctx, void* d_ptr);
+int grrt_trace_items_device_peers(GrrtCtx* ctx, const GrrtDeviceScene* dscene,
+                                  const uint32_t* d_items, uint64_t n_items,
+                                  uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
+                                  uint32_t samples_per_axis, uint32_t n_peers,
+                                  double* const* d_xyza_peers, uint8_t* const* d_class_peers,
+                                  uint8_t* const* d_stop_peers, uint64_t* d_counters, void* cuda_stream);
+
 /* resolve_minimum_luminance + collect_pixels_to_supersample (raytracer.rs:118-129,
  * 386-458) over a complete base buffer of rows x cols pixels on the device.  Writes the
  * flagged pixel ids (ascending, i.e. the reference's row-major push order) to

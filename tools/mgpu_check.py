@@ -21,6 +21,9 @@ for name, w, h in (("C2", 301, 203), ("C1", 96, 64)):
         same = np.array_equal(got, ref["xyza"])
         print(f"{name} {w}x{h} world={world}: bit-identical to 1-GPU frame: {same}; supersampled {c['pixels_supersampled']} vs {ref['stats']['pixels_supersampled']}", flush=True)
         assert same
+    if rank == 0:
+        print('  peer-store path' if fr.p2p else '  all-gather path', flush=True)
+    fr.close()
     eng.close()
 dist.barrier()
 dist.destroy_process_group()

@@ -30,4 +30,7 @@ if rank == 0:
     print("phase", " ".join(f"{k:>12s}" for k in keys))
     for r in range(world):
         print(f"rank{r}", " ".join(f"{v:12.2f}" for v in allt[r].tolist()))
+if rank == 0:
+    print('peer-store path' if fr.p2p else 'all-gather path')
+fr.close()
 dist.barrier(); dist.destroy_process_group()
