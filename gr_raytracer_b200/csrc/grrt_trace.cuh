@@ -1,31 +1,42 @@
 // grrt_trace.cuh -- the persistent ray-tracing kernel (K1/K3 of SURVEY.md section 2).
 //
 // Scheduling: a fixed grid of persistent CTAs; every lane owns one ray at a time and pulls the
-// next work unit from a global atomic counter the moment its ray terminates (one atomicAdd per
+// next work unit from a global atomic counter when its ray has terminated (one atomicAdd per
 // warp, lanes ranked with ballot/popc).  All lanes of a warp therefore execute the same RKF45
-// attempt code on every trip of the main loop regardless of which ray or step they are on, so
-// the 100x spread in steps-per-ray (171 ... 15 500 ... 276 733) never idles a lane; only the
-// rare per-ray events (ray set-up, object shading, terminal colour) diverge.
+// attempt code regardless of which ray or step they are on, so the 100x spread in steps-per-ray
+// (171 ... 15 500 ... 276 733) never idles a lane for long.
 //
-// RKF45 attempt (v2): the six stages run as a real loop -- one copy of the right-hand side in the
-// instruction stream, ~300 SASS instructions per trip -- instead of six inlined copies (v1 was
-// 12.6k instructions for KerrBL and spent 1.4 stall cycles per issue waiting for instruction
-// fetch, profiles/r1_c2_trace_kernel_v1.json).  The stage derivatives k1..k5 live in shared memory
+// Hot loop / events: the kernel is two nested loops.  The inner one runs RKF45 attempts until some
+// lane of the warp has an event (a chord hit an object, a ray ended, a lane is idle); everything
+// that handles events -- shading, the ray-march, terminal colour, write-out, ray set-up -- is
+// outside it, so the code executed thousands of times per ray is one contiguous ~1.5k
+// instructions.  Objects::intersects is split accordingly: its geometric half runs in the loop and
+// records which objects became the nearest hit at their turn; its shading half runs on the event,
+// in the same order, so that emitter errors fail the pixel exactly when the reference's `?` does.
+//
+// RKF45 attempt: the six stages run as a real loop -- one copy of the right-hand side in the
+// instruction stream -- instead of six inlined copies (v1 was 12.6k instructions for KerrBL and
+// spent 1.4 stall cycles per issue waiting for instruction fetch,
+// profiles/r1_c2_trace_kernel_v1.json).  The stage derivatives k1..k5 live in shared memory
 // ([stage][component][thread], conflict-free), the 5th-order solution and the error vector are
 // accumulated in registers as each stage completes -- the same left-to-right order in which
 // runge_kutta.rs:115-123 sums them.  State components whose derivative is identically zero
 // (KerrBL: 6,7; Kerr-Schild: p_t; flat Cartesian: all momenta) are skipped: they contribute exact
-// zeros to every sum of the reference, so nothing changes numerically.
+// zeros to every sum of the reference, so nothing changes numerically; and only the components the
+// right-hand side reads have their k stored.
 //
 // The reference stores the whole trajectory (112 B per step) and walks it a second time
 // (scene.rs:141-152); here each accepted step is tested against the objects as it is produced
-// and only the previous state is kept (in shared memory: it is read only when a hit occurs).
+// and only the previous state is kept (in shared memory: it is read only when a hit is shaded).
 //
-// VolumetricDisc ray-marches are executed warp-cooperatively: the lane that found the hit
-// broadcasts the march, the 32 lanes evaluate 32 consecutive samples in parallel (density,
-// Perlin fBm, redshift, LUT colour) and the order-dependent accumulation (transparency product,
-// emission sums) is then replayed in sample order so the result is the same sequence of
+// VolumetricDisc ray-marches are executed warp-cooperatively: the lane that found the hit hands
+// the march over through shared memory, the 32 lanes evaluate 32 consecutive samples in parallel
+// (density, Perlin fBm, redshift, LUT colour) and the order-dependent accumulation (transparency
+// product, emission sums) is then replayed in sample order so the result is the same sequence of
 // floating-point operations the reference performs (volumetric_disc.rs:209-328).
+//
+// Multi-GPU: with TraceArgs::n_peers > 0 a finished pixel is stored into every rank's frame buffer
+// (peer-mapped over NVLink) instead of a local compact buffer, so no gather pass follows.
 #pragma once
 
 #include "grrt_device.cuh"
@@ -37,14 +48,8 @@ constexpr int kMaxHits = 32;
 constexpr int kMaxRetryStep = 100;  // runge_kutta.rs:60
 constexpr unsigned kFull = 0xffffffffu;
 
-// Fehlberg tableau as data for the stage loop (same expressions as the RK_* constants)
-__constant__ double c_rk_b[6][5] = {
-    {0.0, 0.0, 0.0, 0.0, 0.0},
-    {RK_B21, 0.0, 0.0, 0.0, 0.0},
-    {RK_B31, RK_B32, 0.0, 0.0, 0.0},
-    {RK_B41, RK_B42, RK_B43, 0.0, 0.0},
-    {RK_B51, RK_B52, RK_B53, RK_B54, 0.0},
-    {RK_B61, RK_B62, RK_B63, RK_B64, RK_B65}};
+// Fehlberg weights as data for the stage loop (same expressions as the RK_* constants; the B coefficients are
+// compile-time operands, see rk_b below)
 __constant__ double c_rk_ch[6] = {RK_CH1, RK_CH2, RK_CH3, RK_CH4, RK_CH5, RK_CH6};
 __constant__ double c_rk_ct[6] = {RK_CT1, RK_CT2, RK_CT3, RK_CT4, RK_CT5, RK_CT6};
 
