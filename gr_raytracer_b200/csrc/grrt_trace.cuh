@@ -521,8 +521,17 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                         if (Comp<G>::on(i)) {
                             const double k = h_cur * d[i];
                             if (s < 5 && Comp<G>::stored(i)) kst[Comp<G>::slot(i) * kTraceThreads] = k;
+#ifdef GRRT_FAST_MATH
+                            // CH2 = CT2 = 0 (runge_kutta.rs:43-55): the exact build adds the zeros; skipping them is worth
+                            // 3 % for Schwarzschild (C1 382 -> 370 ms) but costs KerrBL 7 % (register allocation at 96)
+                            if (G == GRRT_GEOM_KERR_BL || s != 1) {
+                                y_new[i] = y_new[i] + ch * k;
+                                acc_e[i] = acc_e[i] + ct * k;
+                            }
+#else
                             y_new[i] = y_new[i] + ch * k;
                             acc_e[i] = acc_e[i] + ct * k;
+#endif
                         }
                     }
                     kst += NC * kTraceThreads;
