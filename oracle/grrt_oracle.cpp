@@ -1642,13 +1642,14 @@ bool vol_precompute_exit(const GrrtObject& o, V3 ro, V3 rd, double& out) {  // :
 }
 // :209-328; returns GRRT_RAYERR_* from compute_temperature (the caller maps it to (0,0,0,0))
 int vol_raymarch(const SceneView& sv, const GrrtObject& o, V3 ro, V3 rd, const Frequency& fr, Cie& out,
-                 uint64_t& samples) {
+                 uint64_t& samples, bool use_cached_exit = true) {
     double sigma_a = o.absorption, sigma_s = o.scattering;
     Cie accum = cie(0.0, 0.0, 0.0, 0.0);
     double transparency = 1.0, alpha_weighted_sum = 0.0, alpha_weight_total = 0.0;
     double d_s = o.vol_step_size, d_o = 0.0;
     double exit_distance = 0.0;
-    bool cached = vol_precompute_exit(o, ro, rd, exit_distance);
+    // raymarch_constant_step_internal(.., use_cached_exit): the production path passes true (:198-207)
+    bool cached = use_cached_exit && vol_precompute_exit(o, ro, rd, exit_distance);
     V3 axis = axis_of(o);
     for (uint64_t i = 0; i < o.vol_max_steps; ++i) {
         V3 p = ro + rd * d_o;
@@ -2167,6 +2168,55 @@ void orc_volumetric_basis(const double axis_in[3], double axis[3], double e1[3],
     e2[0] = E2.x; e2[1] = E2.y; e2[2] = E2.z;
 }
 double orc_volumetric_density(const GrrtObject* o, const double p[3]) { return vol_density(*o, v3(p[0], p[1], p[2])); }
+// ---- extra probes for the reference's unit tests (tests/test_oracle_kat.py) ----
+void orc_ks_metrics(double radius, double a, double x, double y, double z, double cov[16], double contra[16]) {
+    M4 c = ks_metric(radius, a, x, y, z), k = ks_metric_contravariant(radius, a, x, y, z);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            cov[4 * i + j] = c.m[i][j];
+            contra[4 * i + j] = k.m[i][j];
+        }
+}
+void orc_axial_killing_vector(const GrrtGeometry* geom, const double pos[4], double out[4]) {
+    Geom g{geom->kind, geom->radius, geom->a, geom->horizon_epsilon, 0};
+    V4 v = axial_killing_vector(g, v4(pos[0], pos[1], pos[2], pos[3]));
+    for (int i = 0; i < 4; ++i) out[i] = v[i];
+}
+int orc_circular_orbit_velocity(const GrrtGeometry* geom, const double pos[4], double out[4]) {
+    Geom g{geom->kind, geom->radius, geom->a, geom->horizon_epsilon, 0};
+    V4 v;
+    if (!circular_orbit_velocity(g, v4(pos[0], pos[1], pos[2], pos[3]), v)) return 1;
+    for (int i = 0; i < 4; ++i) out[i] = v[i];
+    return 0;
+}
+// Sphere::intersects / VolumetricDisc::intersects on a Cartesian chord: 1 = hit (world-space point, chord parameter)
+int orc_object_intersects(const GrrtObject* o, const double a[3], const double b[3], double hit[3], double* t) {
+    Intersection isec;
+    bool ok = false;
+    V3 ys = v3(a[0], a[1], a[2]), ye = v3(b[0], b[1], b[2]);
+    if (o->kind == GRRT_OBJ_SPHERE) ok = sphere_intersects(*o, ys, ye, isec);
+    else if (o->kind == GRRT_OBJ_VOLUMETRIC_DISC) ok = vol_intersects(*o, ys, ye, isec);
+    else return -1;
+    if (ok) {
+        hit[0] = isec.point[1]; hit[1] = isec.point[2]; hit[2] = isec.point[3];
+        if (t) *t = isec.t;
+    }
+    return ok ? 1 : 0;
+}
+// VolumetricDisc::raymarch_constant_step_internal (volumetric_disc.rs:209-328) with either exit test
+int orc_volumetric_raymarch(const GrrtScene* s, uint32_t object_index, const double ro[3], const double rd[3],
+                            const double freq[3], int use_cached_exit, double xyza[4], uint64_t* samples) {
+    if (object_index >= s->n_objects || s->objects[object_index].kind != GRRT_OBJ_VOLUMETRIC_DISC) return -1;
+    SceneView sv = view_of(s);
+    Frequency fr{freq[0], freq[1], freq[2]};
+    Cie c;
+    uint64_t n = 0;
+    int rc = vol_raymarch(sv, s->objects[object_index], v3(ro[0], ro[1], ro[2]), v3(rd[0], rd[1], rd[2]), fr, c, n,
+                          use_cached_exit != 0);
+    xyza[0] = c.x; xyza[1] = c.y; xyza[2] = c.z; xyza[3] = c.alpha;
+    if (samples) *samples = n;
+    return rc;
+}
 void orc_srgb_to_xyz(uint8_t r, uint8_t g, uint8_t b, double out[4]) {
     Cie c = srgb_to_xyz(r, g, b);
     out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.alpha;

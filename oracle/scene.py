@@ -65,6 +65,11 @@ def lib():
     L.orc_volumetric_basis.argtypes = [dp, dp, dp, dp]
     L.orc_volumetric_density.argtypes = [C.POINTER(abi.GrrtObject), dp]
     L.orc_volumetric_density.restype = d
+    L.orc_ks_metrics.argtypes = [d, d, d, d, d, dp, dp]
+    L.orc_axial_killing_vector.argtypes = [C.POINTER(abi.GrrtGeometry), dp, dp]
+    L.orc_circular_orbit_velocity.argtypes = [C.POINTER(abi.GrrtGeometry), dp, dp]
+    L.orc_object_intersects.argtypes = [C.POINTER(abi.GrrtObject), dp, dp, dp, dp]
+    L.orc_volumetric_raymarch.argtypes = [C.POINTER(abi.GrrtScene), C.c_uint32, dp, dp, dp, C.c_int, dp, C.POINTER(C.c_uint64)]
     L.orc_srgb_to_xyz.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, dp]
     L.orc_blend.argtypes = [dp, dp, dp]
     L.orc_texture_color.argtypes = [C.POINTER(abi.GrrtScene), C.POINTER(abi.GrrtTexture), d, d, d, d, dp]

@@ -557,3 +557,208 @@ def test_perlin_restatement_properties():
     rng = np.random.default_rng(0)
     vals = [L.orc_perlin(perm, *rng.uniform(-50, 50, 3)) for _ in range(2000)]
     assert -1.0 <= min(vals) < -0.3 and 0.3 < max(vals) <= 1.0
+
+
+# ---- more of the reference's unit tests (metric, Killing decomposition, Doppler / Luminet, object geometry) --------
+
+def test_kerr_schild_contravariant_metric_is_the_inverse():
+    """kerr.rs:528-544 (test_metric_contravariant_matches_inverse): tolerance 1e-10 at the three listed points."""
+    for x, y, z in [(3.0, -4.0, 1.5), (-7.5, 2.0, 0.3), (10.0, 1.0, -2.5)]:
+        cov, contra = (C.c_double * 16)(), (C.c_double * 16)()
+        L.orc_ks_metrics(1.0, 0.5, x, y, z, cov, contra)
+        g = np.array(list(cov)).reshape(4, 4)
+        gi = np.array(list(contra)).reshape(4, 4)
+        assert np.allclose(g, g.T, atol=0) and np.abs(gi - np.linalg.inv(g)).max() < 1e-10
+
+
+def _zamo(geom, pos):
+    out = vec4()
+    assert L.orc_resolve_camera_velocity(C.byref(geom), osc.darr(pos), abi.CAMVEL_ZAMO, osc.darr([0.0] * 4), out) == 0
+    return list(out)
+
+
+def _axial(geom, pos):
+    out = vec4()
+    L.orc_axial_killing_vector(C.byref(geom), osc.darr(pos), out)
+    return list(out)
+
+
+def test_zamo_properties_across_charts():
+    """circular_orbit.rs:183-243: normalised, zero angular momentum, reduces to the static observer at a = 0."""
+    a = 0.499
+    for geom, pos in ((osc.make_geometry(abi.GEOM_KERR, 1.0, a, 1e-4), [0.0, 5.0, a, 0.0]),
+                      (osc.make_geometry(abi.GEOM_KERR_BL, 1.0, a, 1e-4), [0.0, 5.0, PI / 2, 0.0])):
+        u, ax = _zamo(geom, pos), _axial(geom, pos)
+        assert ip(geom, pos, u, u) == pytest.approx(-1.0, abs=1e-9)
+        assert ip(geom, pos, u, ax) == pytest.approx(0.0, abs=1e-9)
+    gs = osc.make_geometry(abi.GEOM_SCHWARZSCHILD, 1.0, 0.0, 1e-4)
+    pos_s = [0.0, 5.0, 1.1, 0.3]
+    stat = vec4()
+    assert L.orc_resolve_camera_velocity(C.byref(gs), osc.darr(pos_s), abi.CAMVEL_STATIC, osc.darr([0.0] * 4), stat) == 0
+    assert _zamo(gs, pos_s) == pytest.approx(list(stat), abs=1e-15)
+
+
+@pytest.mark.parametrize("kind,a,pos,probes,time_sign", [
+    (abi.GEOM_SCHWARZSCHILD, 0.0, [0.0, 6.0, PI / 2, 1.1], [[1.0, -0.4, 0.02, 0.05], [-1.3, 0.2, 0.0, -0.08]], 1.0),
+    (abi.GEOM_KERR, 0.499, [0.0, 3.0, -4.0, 0.0], [[1.0, 0.3, -0.2, 0.1], [-0.8, -0.5, 0.4, 0.0]], -1.0),
+    (abi.GEOM_KERR_BL, 0.3, [0.0, 5.0, PI / 2, 0.7], [[1.0, -0.4, 0.02, 0.05], [-1.2, 0.1, -0.03, 0.09]], -1.0),
+])
+def test_killing_decomposition_identities(kind, a, pos, probes, time_sign):
+    """circular_orbit.rs:245-319: u = u_t d_t + u_phi xi_axial, u.u = signature[0], u.p = u_t p_t + u_phi p_phi."""
+    geom = osc.make_geometry(kind, 1.0, a, 1e-4)
+    u = vec4()
+    assert L.orc_circular_orbit_velocity(C.byref(geom), osc.darr(pos), u) == 0
+    u = list(u)
+    ax = _axial(geom, pos)
+    e_t = [1.0, 0.0, 0.0, 0.0]
+    # the Killing coefficients: circular_orbit.rs:39-136 works with the equatorial BL radius of the point
+    r_bl = pos[1] if kind != abi.GEOM_KERR else osc.camera_position_native(osc.make_geometry(abi.GEOM_KERR_BL, 1.0, a, 1e-4),
+                                                                          pos[1:])[1]
+    coeff = (C.c_double * 2)()
+    assert L.orc_circular_orbit(1.0, a, r_bl, coeff) == 0
+    assembled = [coeff[0] * e_t[i] + coeff[1] * ax[i] for i in range(4)]
+    assert u == pytest.approx(assembled, abs=1e-12)
+    assert ip(geom, pos, u, u) == pytest.approx(time_sign, abs=1e-10)
+    for p in probes:
+        direct = ip(geom, pos, u, p)
+        assert direct == pytest.approx(coeff[0] * ip(geom, pos, e_t, p) + coeff[1] * ip(geom, pos, ax, p), abs=1e-10)
+
+
+def _redshift(geom, pos, observer, emitter, momentum, sig0):
+    """RedshiftComputer::compute_redshift_from_energies (redshift.rs:35-37, 69-73)."""
+    return (sig0 * ip(geom, pos, observer, momentum)) / (sig0 * ip(geom, pos, emitter, momentum))
+
+
+def test_doppler_formulas_with_hand_built_momentum():
+    """redshift.rs:116-172: approaching / receding / transverse / at rest, and invariance under p -> -p."""
+    g = osc.make_geometry(abi.GEOM_EUCLIDEAN, 0.0, 0.0, 0.0)
+    pos, p, obs = [0.0] * 4, [-1.0, -1.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0]
+    v = 0.5
+    gam = 1.0 / math.sqrt(1.0 - v * v)
+    cases = {(gam, gam * v, 0.0, 0.0): 1.0 / (gam * (1.0 - v)), (gam, -gam * v, 0.0, 0.0): 1.0 / (gam * (1.0 + v)),
+             (gam, 0.0, gam * v, 0.0): 1.0 / gam, (1.0, 0.0, 0.0, 0.0): 1.0}
+    for em, want in cases.items():
+        assert _redshift(g, pos, obs, list(em), p, -1.0) == pytest.approx(want, abs=1e-12)
+    em = [gam, gam * v, 0.0, 0.0]
+    assert _redshift(g, pos, obs, em, p, -1.0) == pytest.approx(_redshift(g, pos, obs, em, [-c for c in p], -1.0), abs=1e-15)
+
+
+def test_disc_redshift_matches_luminet_closed_form():
+    """redshift.rs:183-243: 1 + z = (1 - 3M/r)^(-1/2) (1 + Omega L/E) for a circular-orbit emitter in Schwarzschild."""
+    g = osc.make_geometry(abi.GEOM_SCHWARZSCHILD, 1.0, 0.0, 1e-4)
+    m = 0.5
+    for r in (2.0, 3.0, 5.0, 10.0):
+        a = 1.0 - 1.0 / r
+        omega = math.sqrt(m / r ** 3)
+        u_t = 1.0 / math.sqrt(1.0 - 3.0 * m / r)
+        for phi in (0.3, 2.0, 4.5):
+            pos = [0.0, r, PI / 2, phi]
+            u = vec4()
+            assert L.orc_circular_orbit_velocity(C.byref(g), osc.darr(pos), u) == 0
+            u = list(u)
+            for p_r, p_phi_hat in ((-0.7, 0.4), (-0.2, -0.9), (0.5, 0.6), (0.0, 1.0)):
+                p_phi = p_phi_hat / r
+                spatial = p_r * p_r / a + r * r * p_phi * p_phi
+                p = [-math.sqrt(spatial / a), p_r, 0.0, p_phi]
+                assert ip(g, pos, p, p) == pytest.approx(0.0, abs=1e-12)
+                e_c, l_c = a * p[0], -r * r * p_phi
+                emitter_energy = ip(g, pos, u, p)
+                assert emitter_energy == pytest.approx(u_t * (e_c + omega * l_c), abs=1e-10)
+                assert e_c / emitter_energy == pytest.approx(math.sqrt(1.0 - 3.0 * m / r) / (1.0 + omega * l_c / e_c), abs=1e-10)
+
+
+def test_gravitational_redshift_analytic_without_integration():
+    """redshift.rs:253-300: radial null ray, static emitter at r = 3 seen by a static camera at r = 10:
+    g = sqrt(a_em / a_cam)."""
+    g = osc.make_geometry(abi.GEOM_SCHWARZSCHILD, 1.0, 0.0, 1e-4)
+    r_cam, r_em, p_t = 10.0, 3.0, -1.0
+    a_cam, a_em = 1.0 - 1.0 / r_cam, 1.0 - 1.0 / r_em
+    pos_c, pos_e = [0.0, r_cam, PI / 2, 0.0], [0.0, r_em, PI / 2, 0.0]
+    p_c, p_e = [p_t / a_cam, p_t, 0.0, 0.0], [p_t / a_em, p_t, 0.0, 0.0]
+    assert ip(g, pos_c, p_c, p_c) == pytest.approx(0.0, abs=1e-12) and ip(g, pos_e, p_e, p_e) == pytest.approx(0.0, abs=1e-12)
+    stat = lambda pos: [1.0 / math.sqrt(1.0 - 1.0 / pos[1]), 0.0, 0.0, 0.0]
+    shift = ip(g, pos_c, stat(pos_c), p_c) / ip(g, pos_e, stat(pos_e), p_e)
+    assert shift == pytest.approx(math.sqrt(a_em / a_cam), abs=1e-12)
+
+
+def _sphere_object(x, y, z, radius=1.0):
+    o = abi.GrrtObject()
+    o.kind = abi.OBJ_SPHERE
+    o.texture = checker(0.0, 2.0, 2.0, (100, 0, 0), (0, 100, 0))
+    o.radius = radius
+    o.position[:] = [x, y, z]
+    return o
+
+
+def _hits(o, a, b):
+    hit, t = (C.c_double * 3)(), C.c_double()
+    rc = L.orc_object_intersects(C.byref(o), osc.darr(a), osc.darr(b), hit, C.byref(t))
+    assert rc in (0, 1)
+    return (list(hit), t.value) if rc else None
+
+
+def test_sphere_intersections():
+    """sphere.rs:188-246: a chord is a hit only if it crosses the surface; the hit point is in world space."""
+    assert _hits(_sphere_object(0, 0, 0), [1.1, 0, 0], [0.9, 0, 0]) is not None
+    assert _hits(_sphere_object(0, 0, 0), [1.1, 0, 0], [1.01, 0, 0]) is None
+    assert _hits(_sphere_object(5, 0, 0), [6.1, 0, 0], [5.9, 0, 0]) is not None
+    assert _hits(_sphere_object(5, 0, 0), [6.1, 0, 0], [6.01, 0, 0]) is None
+    hit, _ = _hits(_sphere_object(0, 0, 20), [0, 0, 22.0], [0, 0, 19.5])
+    assert hit[2] == pytest.approx(21.0, abs=1e-9)
+
+
+def _reference_test_volumetric_disc(colour=None):
+    """create_disc of volumetric_disc.rs:666-691 (Checker red/blue) or the FixedTextureMap variant (:741-760)."""
+    o = abi.GrrtObject()
+    o.kind = abi.OBJ_VOLUMETRIC_DISC
+    o.texture = checker(3.0, 5.0, 5.0, (255, 0, 0), (0, 0, 255))
+    if colour is not None:   # a texture that answers the same CIE value everywhere
+        o.texture.c1[:] = colour
+        o.texture.c2[:] = colour
+        o.texture.beaming_exponent = 0.0
+    o.temperature.kind = abi.TEMP_CONSTANT   # DummyTemperatureComputer: 1000 K at every radius
+    o.temperature.constant = 1000.0
+    o.inner_radius, o.outer_radius = 1.0, 3.0
+    ax, e1, e2 = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_double * 3)()
+    L.orc_volumetric_basis(osc.darr([0.0, 0.0, 1.0]), ax, e1, e2)
+    o.axis[:], o.e1[:], o.e2[:] = list(ax), list(e1), list(e2)
+    o.num_octaves, o.vol_max_steps, o.vol_step_size, o.thickness = 4, 500, 0.01, 0.5
+    o.density_multiplier, o.brightness_reference_temperature = 10.0, 1000.0
+    o.absorption, o.scattering = 0.2, 0.2
+    o.noise_scale[:] = [1.0, 1.0, 1.0]
+    o.noise_offset = 1.0
+    perm = (C.c_uint8 * 256)()
+    L.orc_perlin_permutation(42, perm)
+    o.perlin_perm[:] = list(perm)
+    return o
+
+
+def test_volumetric_disc_geometry_and_density():
+    """volumetric_disc.rs:693-721: a radial chord through the gas hits, one above the caps misses; density is
+    positive inside and exactly zero outside the radii / the slab."""
+    o = _reference_test_volumetric_disc()
+    assert _hits(o, [0.5, 0, 0], [1.5, 0, 0]) is not None
+    assert _hits(o, [1.5, 0, 2.0], [2.5, 0, 2.0]) is None
+    dens = lambda p: L.orc_volumetric_density(C.byref(o), osc.darr(p))
+    assert dens([2.0, 0.0, 0.0]) > 0.0
+    assert dens([0.2, 0.0, 0.0]) == 0.0 and dens([2.0, 0.0, 2.0]) == 0.0
+
+
+def test_volumetric_raymarch_opacity_and_cached_exit_matches_legacy():
+    """volumetric_disc.rs:723-786: 0 < alpha <= 1 for a march through the gas; the cached exit distance gives the
+    result of the per-step exit test to 1e-10."""
+    g = osc.make_geometry(abi.GEOM_EUCLIDEAN, 0.0, 0.0, 0.0)
+    cam = osc.make_camera(g, [0.0, 10.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0], PI / 2, 3, 3)
+    freq = osc.darr([1.0, 1.0, 0.0])   # unit_frequency(): observer_energy 1, p_t 1, p_phi 0
+    for colour in (None, [2.0, 1.0, 0.5, 0.7]):
+        sc = reference_test_scene(g, cam, 0.1, 3.0, 4.0)
+        sc.c.objects[0] = _reference_test_volumetric_disc(colour)
+        out = {}
+        for cached in (1, 0):
+            xyza, n = (C.c_double * 4)(), C.c_uint64()
+            rc = L.orc_volumetric_raymarch(C.byref(sc.c), 0, osc.darr([2.0, 0.0, 0.0]), osc.darr([1.0, 0.0, 0.0]), freq,
+                                           cached, xyza, C.byref(n))
+            assert rc == 0
+            out[cached] = list(xyza)
+        assert 0.0 < out[1][3] <= 1.0
+        assert out[1] == pytest.approx(out[0], abs=1e-10)
