@@ -84,6 +84,10 @@ def lib():
         L.grrt_host_scene_get.restype = scene_p
         L.grrt_host_scene_free.argtypes = [vp]
         L.grrt_host_scene_set_camera.argtypes = [vp, C.POINTER(abi.GrrtCliOpts), C.c_char_p, C.c_size_t]
+        L.grrt_host_blackbody_xyz.argtypes = [C.c_double, C.c_double, dp]
+        L.grrt_host_blackbody_xyz.restype = None
+        L.grrt_host_xyz_to_srgb8.argtypes = [dp, C.c_double, u8p]
+        L.grrt_host_xyz_to_srgb8.restype = None
         L.grrt_host_ray_at.argtypes = [C.POINTER(abi.GrrtGeometry), dp, dp, dp, dp, C.c_char_p, C.c_size_t]
         L.grrt_host_write_ray_csv.argtypes = [C.POINTER(abi.GrrtGeometry), C.POINTER(abi.GrrtStep), C.c_uint64, C.c_char_p]
         L.grrt_host_write_png_rgb8.argtypes = [C.c_char_p, u8p, C.c_uint32, C.c_uint32]

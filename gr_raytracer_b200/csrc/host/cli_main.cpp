@@ -7,6 +7,9 @@
 //      | render-ray --row R --col C [--filename rendered-ray.csv]
 //      | render-ray-at --position x,y,z --direction x,y,z [--filename rendered-ray-at.csv]
 //      | render-frames --camera-positions positions.csv [--output-pattern frame_%05d.png] [--first K --stride S --count N]
+//      | blackbody --temperature T [--redshift g]
+//      | blackbody-spectrum [--min-temperature 1000 --max-temperature 10000 --min-redshift 0.5 --max-redshift 2
+//                            --width 1000 --height 1000 --filename blackbody_spectrum.png]
 //
 // Extra (not in the reference): --resource-root DIR (prefix for relative texture paths), --device N, and
 // render-frames: the reference's camera fly-through (scripts/Readme.md) runs the binary once per camera position;
@@ -16,6 +19,7 @@
 // split a movie over N GPUs.
 #include <chrono>
 #include <fstream>
+#include <algorithm>
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
@@ -58,6 +62,9 @@ int main(int argc, char** argv) {
     grrt_cli_opts_default(&opts);
     std::string config_file, action, filename, resource_root, positions_file, output_pattern = "frame_%05d.png";
     long long first_frame = 0, frame_stride = 1, frame_count = -1;
+    double bb_temperature = -1.0, bb_redshift = 1.0, bb_tmin = 1000.0, bb_tmax = 10000.0, bb_gmin = 0.5, bb_gmax = 2.0;
+    bool size_given = false, short_r_given = false;
+    std::string short_r_value;
     long long from_row = -1, from_col = -1, to_row = -1, to_col = -1, ray_row = -1, ray_col = -1;
     std::vector<double> at_pos, at_dir;
     int device = 0;
@@ -74,8 +81,14 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < args.size(); ++i) {
         std::string a = args[i];
         std::string flag = a.substr(0, a.find('='));
-        if (flag == "--width") opts.width = std::atoll(value(i, flag).c_str());
-        else if (flag == "--height") opts.height = std::atoll(value(i, flag).c_str());
+        if (flag == "--width") { opts.width = std::atoll(value(i, flag).c_str()); size_given = true; }
+        else if (flag == "--height") { opts.height = std::atoll(value(i, flag).c_str()); size_given = true; }
+        else if (flag == "--temperature" || flag == "-t") bb_temperature = std::atof(value(i, flag).c_str());
+        else if (flag == "--redshift") bb_redshift = std::atof(value(i, flag).c_str());
+        else if (flag == "--min-temperature") bb_tmin = std::atof(value(i, flag).c_str());
+        else if (flag == "--max-temperature") bb_tmax = std::atof(value(i, flag).c_str());
+        else if (flag == "--min-redshift") bb_gmin = std::atof(value(i, flag).c_str());
+        else if (flag == "--max-redshift") bb_gmax = std::atof(value(i, flag).c_str());
         else if (flag == "--step-size") opts.step_size = std::atof(value(i, flag).c_str());
         else if (flag == "--max-steps") opts.max_steps = std::strtoull(value(i, flag).c_str(), nullptr, 10);
         else if (flag == "--max-radius") opts.max_radius = std::atof(value(i, flag).c_str());
@@ -109,7 +122,8 @@ int main(int argc, char** argv) {
         else if (flag == "--from-col") from_col = std::atoll(value(i, flag).c_str());
         else if (flag == "--to-row") to_row = std::atoll(value(i, flag).c_str());
         else if (flag == "--to-col") to_col = std::atoll(value(i, flag).c_str());
-        else if (flag == "--row" || flag == "-r") ray_row = std::atoll(value(i, flag).c_str());
+        else if (flag == "--row") ray_row = std::atoll(value(i, flag).c_str());
+        else if (flag == "-r") { short_r_value = value(i, flag); short_r_given = true; }
         else if (flag == "--col") ray_col = std::atoll(value(i, flag).c_str());
         else if (flag == "--position" || flag == "-p") at_pos = parse_list(value(i, flag), "--position");
         else if (flag == "--direction" || flag == "-d") at_dir = parse_list(value(i, flag), "--direction");
@@ -118,11 +132,58 @@ int main(int argc, char** argv) {
         else if (flag == "--first") first_frame = std::atoll(value(i, flag).c_str());
         else if (flag == "--stride") frame_stride = std::atoll(value(i, flag).c_str());
         else if (flag == "--count") frame_count = std::atoll(value(i, flag).c_str());
-        else if (a == "render" || a == "render-ray" || a == "render-ray-at" || a == "render-frames") action = a;
-        else if (a == "blackbody" || a == "blackbody-spectrum") die("subcommand '" + a + "' is not part of the geodesic path and is not provided by grrt");
+        else if (a == "render" || a == "render-ray" || a == "render-ray-at" || a == "render-frames" || a == "blackbody" ||
+                 a == "blackbody-spectrum") action = a;
         else die("unexpected argument '" + a + "'");
     }
-    if (action.empty()) die("a subcommand is required: render | render-ray | render-ray-at | render-frames");
+    if (action.empty()) die("a subcommand is required: render | render-ray | render-ray-at | render-frames | blackbody | blackbody-spectrum");
+    if (short_r_given) {  // clap: -r is --row of render-ray and --redshift of blackbody
+        if (action == "blackbody") bb_redshift = std::atof(short_r_value.c_str());
+        else ray_row = std::atoll(short_r_value.c_str());
+    }
+
+    // ---- cli/blackbody.rs: no scene; `blackbody` needs no GPU either ----
+    if (action == "blackbody") {
+        if (bb_temperature < 0.0) die("the following required arguments were not provided: --temperature <TEMPERATURE>");
+        double xyz[3];
+        uint8_t c[3];
+        grrt_host_blackbody_xyz(bb_temperature, bb_redshift, xyz);
+        grrt_host_xyz_to_srgb8(xyz, 1.0, c);
+        std::printf("Blackbody color at T=%gK (redshift=%g):\n", bb_temperature, bb_redshift);
+        std::printf("XYZ:  %.4f, %.4f, %.4f\n", xyz[0], xyz[1], xyz[2]);
+        std::printf("sRGB: R=%d, G=%d, B=%d\n", c[0], c[1], c[2]);
+        std::printf("sRGB: R=%.4f, G=%.4f, B=%.4f\n", c[0] / 255.0, c[1] / 255.0, c[2] / 255.0);
+        std::printf("Color block: \x1b[48;2;%d;%d;%dm      \x1b[0m\n", c[0], c[1], c[2]);
+        return 0;
+    }
+    if (action == "blackbody-spectrum") {
+        const uint32_t W = size_given ? (uint32_t)opts.width : 1000u, H = size_given ? (uint32_t)opts.height : 1000u;
+        if (W == 0 || H == 0) die("Invalid configuration: --width and --height must be positive");
+        if (filename.empty()) filename = "blackbody_spectrum.png";
+        const size_t n = (size_t)W * H;
+        std::vector<double> xyza(4 * n);
+        unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; ++t)
+            pool.emplace_back([&, t] {
+                for (size_t i = t; i < n; i += nt) {  // temperature along x, redshift along y (blackbody.rs:62-71)
+                    double x = (double)(i % W), y = (double)(i / W);
+                    double temperature = bb_tmin + x * (bb_tmax - bb_tmin) / ((double)W - 1.0);
+                    double redshift = bb_gmin + y * (bb_gmax - bb_gmin) / ((double)H - 1.0);
+                    grrt_host_blackbody_xyz(temperature, redshift, &xyza[4 * i]);
+                    xyza[4 * i + 3] = 1.0;
+                }
+            });
+        for (auto& th : pool) th.join();
+        GrrtCtx* bctx = nullptr;
+        if (grrt_init(device, &bctx) != 0) die("no usable CUDA device (sm_100): grrt has no CPU fallback");
+        std::vector<uint8_t> rgb(3 * n);
+        if (grrt_tonemap(bctx, xyza.data(), n, opts.tone_mapping, 1.0, rgb.data())) die(grrt_last_error(bctx));
+        grrt_destroy(bctx);
+        if (grrt_host_write_png_rgb8(filename.c_str(), rgb.data(), W, H)) die("I/O error: cannot write " + filename);
+        std::printf("Saved blackbody spectrum to %s\n", filename.c_str());
+        return 0;
+    }
     if (config_file.empty()) die("Invalid configuration: Config file is required for this action");
 
     auto t0 = std::chrono::steady_clock::now();

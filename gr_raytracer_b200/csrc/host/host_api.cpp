@@ -81,6 +81,13 @@ int grrt_host_scene_set_camera(GrrtHostScene* hs, const GrrtCliOpts* opts, char*
     return rc;
 }
 
+void grrt_host_blackbody_xyz(double temperature, double redshift, double xyz_out[3]) {
+    if (xyz_out) blackbody_xyz_redshifted(temperature, redshift, xyz_out);
+}
+void grrt_host_xyz_to_srgb8(const double xyz[3], double exposure, uint8_t rgb_out[3]) {
+    if (xyz && rgb_out) xyz_to_srgb8(xyz, exposure, rgb_out);
+}
+
 int grrt_host_ray_at(const GrrtGeometry* geometry, const double position_cartesian[3], const double direction_cartesian[3],
                      double pos_out[4], double mom_out[4], char* err, size_t err_len) {
     if (!geometry || !position_cartesian || !direction_cartesian || !pos_out || !mom_out) return GRRT_ERR_INVALID_ARGUMENT;

@@ -658,6 +658,22 @@ void enum_variant(const TomlValue& v, const char* what, std::string& name, const
 
 }  // namespace
 
+// get_cie_xyz_of_black_body_redshifted (black_body_radiation.rs:12-41) for the `blackbody` utilities
+void blackbody_xyz_redshifted(double temperature, double redshift, double out[3]) { blackbody_xyz(temperature, redshift, out); }
+
+// xyz_to_srgb (color.rs:218-233): IEC 2003 matrix, exposure, clamp, sRGB companding, round -- no tone mapping
+void xyz_to_srgb8(const double xyz[3], double exposure, uint8_t rgb[3]) {
+    const double m[3][3] = {{3.2406255, -1.5372080, -0.4986286}, {-0.9689307, 1.8757561, 0.0415175}, {0.0557101, -0.2040211, 1.0569959}};
+    for (int k = 0; k < 3; ++k) {
+        double lin = ((m[k][0] * xyz[0] + m[k][1] * xyz[1]) + m[k][2] * xyz[2]) * exposure;
+        lin = lin > 0.0 ? lin : 0.0;
+        double enc = lin <= 0.0031308 ? 12.92 * lin : 1.055 * std::pow(lin, 1.0 / 2.4) - 0.055;
+        enc = enc < 0.0 ? 0.0 : (enc > 1.0 ? 1.0 : enc);
+        rgb[k] = (uint8_t)std::round(enc * 255.0);
+    }
+}
+
+
 // =========================================================================================================
 // resolve_camera_velocity + assert_future_directed (cli/shared.rs:23-86)
 Vec4 resolve_camera_velocity(const HostGeometry& geo, const Vec4& pos, const std::string& mode, const double explicit_components[4]) {

@@ -38,5 +38,7 @@ int update_camera(HostSceneData& scene, const GrrtCliOpts& opts, std::string& er
 int ray_at(const GrrtGeometry& g, const double position_cartesian[3], const double direction[3], double pos_out[4],
            double mom_out[4], std::string& err);
 void step_to_cartesian(const GrrtGeometry& g, const double x[4], double out[4]);
+void blackbody_xyz_redshifted(double temperature, double redshift, double out[3]);
+void xyz_to_srgb8(const double xyz[3], double exposure, uint8_t rgb[3]);
 
 }  // namespace grrt_host

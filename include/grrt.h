@@ -374,6 +374,11 @@ void grrt_host_scene_free(GrrtHostScene* hs);
 /* Recomputes only the camera of an assembled scene (position, phi/theta/psi, width and
  * height of `opts`; cli/shared.rs:23-86 + Camera::new): one call per animation frame. */
 int grrt_host_scene_set_camera(GrrtHostScene* hs, const GrrtCliOpts* opts, char* err, size_t err_len);
+/* The `blackbody` / `blackbody-spectrum` utilities (cli/blackbody.rs): CIE XYZ of a red-shifted
+ * black body (black_body_radiation.rs:12-41, the integral the black-body LUT is built from) and
+ * xyz_to_srgb (color.rs:218-233: matrix, exposure, clamp, companding; no tone mapping). */
+void grrt_host_blackbody_xyz(double temperature, double redshift, double xyz_out[3]);
+void grrt_host_xyz_to_srgb8(const double xyz[3], double exposure, uint8_t rgb_out[3]);
 /* render-ray-at: momentum from a Cartesian direction in the unboosted tetrad
  * (cli/schwarzschild.rs:89-121, cli/kerr.rs:77-100, cli/kerr_bl.rs:78-107). */
 int grrt_host_ray_at(const GrrtGeometry* geometry, const double position_cartesian[3],

@@ -73,3 +73,25 @@ def test_cli_errors(tmp_path):
     assert r.returncode != 0 and "Config file not found" in r.stderr                   # main.rs:67-73
     r = run(["--camera-position=1,2", "--config-file", os.path.join(ROOT, "scenes/kerr.toml"), "render"], tmp_path)
     assert r.returncode != 0 and "length 3" in r.stderr                                # main.rs:85-89
+
+
+def test_blackbody_spectrum_png_matches_oracle(tmp_path):
+    """cli/blackbody.rs run_blackbody_spectrum: temperature along x, redshift along y, tone-mapped on the device."""
+    from PIL import Image
+    W, H = 24, 10
+    r = run(["--tone-mapping", "global-linear", "blackbody-spectrum", "--width", str(W), "--height", str(H), "--min-temperature",
+             "1500", "--max-temperature", "9000", "--filename", "bb.png"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    img = np.array(Image.open(tmp_path / "bb.png"))
+    assert img.shape == (H, W, 3)
+    xyza = np.zeros((H * W, 4))
+    out = (osc.C.c_double * 4)()
+    for i in range(H * W):
+        t = 1500.0 + (i % W) * (9000.0 - 1500.0) / (W - 1.0)
+        g = 0.5 + (i // W) * (2.0 - 0.5) / (H - 1.0)
+        osc.lib().orc_blackbody_xyz(t, g, out)
+        xyza[i] = [out[0], out[1], out[2], 1.0]
+    ref = np.zeros((H * W, 3), dtype=np.uint8)
+    osc.lib().orc_tonemap(osc.dptr(xyza), H * W, abi.TONEMAP_GLOBAL_LINEAR, 1.0, osc.u8ptr(ref))
+    diff = np.abs(img.reshape(-1, 3).astype(int) - ref.astype(int))
+    assert diff.max() <= 1

@@ -262,3 +262,37 @@ def test_camera_update_equals_fresh_assembly(name):
         assert bytes(sc.c.camera) == before
     sc.close()
     fresh.close()
+
+
+def test_blackbody_utilities_match_oracle_and_reference_kat(tmp_path):
+    """cli/blackbody.rs on the host code of libgrrt: the XYZ integral and xyz_to_srgb agree with the oracle bit for
+    bit, reproduce the reference's known colours (black_body_radiation.rs:63-73) and the `blackbody` subcommand
+    prints them in the reference's format."""
+    import subprocess
+    L, O = api.lib(), osc.lib()
+    for temp, shift in ((1000.0, 1.0), (10000.0, 1.0), (4500.0, 0.7), (6500.0, 1.8)):
+        got, want = (C.c_double * 3)(), (C.c_double * 4)()
+        L.grrt_host_blackbody_xyz(temp, shift, got)
+        O.orc_blackbody_xyz(temp, shift, want)
+        assert list(got) == list(want)[:3]
+        for exposure in (1.0, 1.0 / sum(got)):
+            a, b = (C.c_uint8 * 3)(), (C.c_uint8 * 3)()
+            L.grrt_host_xyz_to_srgb8(got, exposure, a)
+            O.orc_xyz_to_srgb(want, exposure, b)
+            assert tuple(a) == tuple(b)
+    for temp, exp in ((1000.0, (255, 60, 0)), (10000.0, (137, 146, 172))):
+        xyz, rgb = (C.c_double * 3)(), (C.c_uint8 * 3)()
+        L.grrt_host_blackbody_xyz(temp, 1.0, xyz)
+        L.grrt_host_xyz_to_srgb8(xyz, 1.0 / sum(xyz), rgb)
+        assert tuple(rgb) == exp
+    exe = os.path.join(ROOT, "gr_raytracer_b200", "grrt")
+    r = subprocess.run([exe, "blackbody", "--temperature", "6500", "-r", "0.9"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    xyz, rgb = (C.c_double * 3)(), (C.c_uint8 * 3)()
+    L.grrt_host_blackbody_xyz(6500.0, 0.9, xyz)
+    L.grrt_host_xyz_to_srgb8(xyz, 1.0, rgb)
+    assert lines[0] == "Blackbody color at T=6500K (redshift=0.9):"
+    assert lines[1] == "XYZ:  %.4f, %.4f, %.4f" % tuple(xyz)
+    assert lines[2] == "sRGB: R=%d, G=%d, B=%d" % tuple(rgb)
+    assert subprocess.run([exe, "blackbody"], capture_output=True, text=True).returncode != 0
