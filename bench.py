@@ -383,6 +383,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H, "l2": "256 MiB flush write between timed steps",
                        "partition": "whole frame" if world == 1 else f"8x4 tiles round-robin over {world} ranks",
+                       "exchange": "none" if world == 1 else ("peer stores from the trace kernel (cudaIpc over NVLink)"
+                                                              if fr.p2p else "NCCL all-gather"),
                        "textures": "synthetic 2048x2048 atlases (scenes/make_textures.py)"},
             "rays_per_step": rays_per_step, "pixels_supersampled": counts["pixels_supersampled"],
             "rkf45_steps_per_s": accepted / secs, "rkf45_attempts_per_s": attempts / secs, "raymarch_samples_per_s": samples / secs,
