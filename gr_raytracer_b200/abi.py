@@ -35,6 +35,7 @@ ERR_OUT_OF_MEMORY = -8
 ERR_LUT = -9
 
 MAX_OBJECTS = 8
+MAX_PEERS = 8      # GRRT_MAX_PEERS: ranks whose frame buffers one kernel launch can store into
 BLACKBODY_LUT_N = 1000
 TEMPERATURE_LUT_N = 1000
 

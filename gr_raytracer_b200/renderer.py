@@ -128,7 +128,7 @@ class FrameRenderer:
         self.rect = (0, 0, self.H, self.W)
         self.p2p = False
         self._own, self._opened = [], []
-        if world > 1 and getattr(engine, "supports_peers", False) and os.environ.get("GRRT_P2P", "1") != "0":
+        if 1 < world <= abi.MAX_PEERS and getattr(engine, "supports_peers", False) and os.environ.get("GRRT_P2P", "1") != "0":
             self._setup_peer_frames()
         if not self.p2p:
             self.xyza = engine.new((n, 4), torch.float64)
