@@ -23,7 +23,8 @@ class GrrtError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libgrrt.so")
+    # GRRT_LIB: developer knob, points at an alternative build of the same library (tools/variants.py)
+    return os.environ.get("GRRT_LIB") or os.path.join(_HERE, "libgrrt.so")
 
 
 def lib():

@@ -380,8 +380,10 @@ struct RayConst {  // KerrBL per-ray constants of motion (kerr_bl.rs:120-126)
     double e, l_z, q;
 };
 
+// right-hand side with sin(theta), cos(theta) of the state supplied by the caller (spherical / Boyer-Lindquist
+// charts read theta through them only; the Cartesian charts ignore them)
 template <int G>
-GD void geodesic_rhs(const DScene& S, const RayConst& C, const double* y, double* d) {
+GD void geodesic_rhs_trig(const DScene& S, const RayConst& C, const double* y, double sin_theta, double cos_theta, double* d) {
     if (G == GRRT_GEOM_EUCLIDEAN) {  // euclidean.rs:46-53
         d[0] = y[4]; d[1] = y[5]; d[2] = y[6]; d[3] = y[7];
         d[4] = 0.0; d[5] = 0.0; d[6] = 0.0; d[7] = 0.0;
@@ -389,8 +391,7 @@ GD void geodesic_rhs(const DScene& S, const RayConst& C, const double* y, double
         // schwarzschild.rs:54-80, euclidean_spherical.rs:46-70
         double r = y[1];
         double v_t = y[4], v_r = y[5], v_theta = y[6], v_phi = y[7];
-        double s, c;
-        sincos_pi2(y[2], &s, &c);
+        const double s = sin_theta, c = cos_theta;
 #ifdef GRRT_FAST_MATH
         {   // same formulas with shared reciprocals (3 instead of 5-6 divisions)
             const double inv_r = frcp(r), inv_s = frcp(s);
@@ -434,8 +435,7 @@ GD void geodesic_rhs(const DScene& S, const RayConst& C, const double* y, double
     } else if (G == GRRT_GEOM_KERR_BL) {  // kerr_bl.rs:141-174
         double r = y[1], v_r = y[4], v_theta = y[5];
         double a = S.a, r_s = S.radius;
-        double sin_t, cos_t;
-        sincos_pi2(y[2], &sin_t, &cos_t);
+        const double sin_t = sin_theta, cos_t = cos_theta;
         double del = bl_delta(r, r_s, a);
         double rr_aa = r * r + a * a;
         double p_r = rr_aa * C.e - a * C.l_z;
@@ -545,6 +545,33 @@ GD void geodesic_rhs(const DScene& S, const RayConst& C, const double* y, double
         d[4] = 0.0; d[5] = acc[0]; d[6] = acc[1]; d[7] = acc[2];
     }
 }
+
+template <int G>
+GD void geodesic_rhs(const DScene& S, const RayConst& C, const double* y, double* d) {
+    double s = 0.0, c = 1.0;
+    if (GeomTraits<G>::chart != CH_CART) sincos_pi2(y[2], &s, &c);
+    geodesic_rhs_trig<G>(S, C, y, s, c, d);
+}
+
+#ifdef GRRT_FAST_MATH
+// sin and cos of a small angle, |x| <= 1/8: Taylor polynomials (truncation < 3e-18 for sin, 3e-20 for cos), no range
+// reduction.  Used by the stage loop of the FMA build, where the polar angle of a stage argument differs from the
+// angle of the state by the small increment sum B k.
+__constant__ double c_trig_small[8] = {
+    -1.66666666666666666667e-01, 8.33333333333333333333e-03, -1.98412698412698412698e-04, 2.75573192239858906526e-06,   // sin
+    4.16666666666666666667e-02, -1.38888888888888888889e-03, 2.48015873015873015873e-05, -2.75573192239858906526e-07};  // cos
+GD void sincos_small(double x, double* sn, double* cs) {
+    const double z = x * x;
+    double p = fma(z, c_trig_small[3], c_trig_small[2]);
+    p = fma(z, p, c_trig_small[1]);
+    p = fma(z, p, c_trig_small[0]);
+    *sn = fma(x * z, p, x);
+    double q = fma(z, c_trig_small[7], c_trig_small[6]);
+    q = fma(z, q, c_trig_small[5]);
+    q = fma(z, q, c_trig_small[4]);
+    *cs = fma(z * z, q, fma(-0.5, z, 1.0));
+}
+#endif
 
 // GeodesicSolver::momentum_from_state: contravariant momentum of a state
 template <int G>

@@ -4,4 +4,13 @@
 // the oracle by the parity tests.  Kerr-Schild is not built here: it needs the exact kernels.
 #define GRRT_NS grrt_fast
 #define GRRT_FAST_MATH 1
+// the six RKF45 stages as straight-line code (their right-hand sides are ~100 instructions each here; the exact build
+// keeps the stage loop because of the 2000-instruction Kerr-Schild right-hand side), and sin/cos of a stage's polar
+// angle from the state's by the addition theorem (grrt_trace.cuh)
+#ifndef GRRT_NO_UNROLL_STAGES
+#define GRRT_UNROLL_STAGES 1
+#endif
+#ifndef GRRT_NO_SINCOS_DELTA
+#define GRRT_SINCOS_DELTA 1
+#endif
 #include "grrt_kern_impl.cuh"

@@ -53,6 +53,11 @@ constexpr unsigned kFull = 0xffffffffu;
 __constant__ double c_rk_ch[6] = {RK_CH1, RK_CH2, RK_CH3, RK_CH4, RK_CH5, RK_CH6};
 __constant__ double c_rk_ct[6] = {RK_CT1, RK_CT2, RK_CT3, RK_CT4, RK_CT5, RK_CT6};
 
+// the B coefficients as data as well: FP64 instructions take 64-bit constants only from the constant bank (an immediate
+// costs two UMOV), so the unrolled stage code of the FMA build reads them as c[bank][offset] operands
+__constant__ double c_rk_b[25] = {RK_B21, 0, 0, 0, 0, RK_B31, RK_B32, 0, 0, 0, RK_B41, RK_B42, RK_B43, 0, 0,
+                                  RK_B51, RK_B52, RK_B53, RK_B54, 0, RK_B61, RK_B62, RK_B63, RK_B64, RK_B65};
+
 // which of the 8 state components have a non-zero derivative
 template <int G>
 struct Comp {
@@ -85,8 +90,19 @@ __host__ __device__ constexpr double rk_b(int s, int j) {
          : s == 4 ? (j == 0 ? RK_B51 : j == 1 ? RK_B52 : j == 2 ? RK_B53 : RK_B54)
                   : (j == 0 ? RK_B61 : j == 1 ? RK_B62 : j == 2 ? RK_B63 : j == 3 ? RK_B64 : RK_B65);
 }
+__host__ __device__ constexpr double rk_ch(int s) {
+    return s == 0 ? RK_CH1 : s == 1 ? RK_CH2 : s == 2 ? RK_CH3 : s == 3 ? RK_CH4 : s == 4 ? RK_CH5 : RK_CH6;
+}
+__host__ __device__ constexpr double rk_ct(int s) {
+    return s == 0 ? RK_CT1 : s == 1 ? RK_CT2 : s == 2 ? RK_CT3 : s == 3 ? RK_CT4 : s == 4 ? RK_CT5 : RK_CT6;
+}
 // argument of stage SS: y + B_s1 k1 + B_s2 k2 + ... summed left to right (runge_kutta.rs:95-124); straight-line so
 // that all shared-memory loads of a stage are issued together and the coefficients are instruction operands
+#if defined(GRRT_FAST_MATH) && defined(GRRT_UNROLL_STAGES)
+#define RKB(SS, j) c_rk_b[((SS) - 1) * 5 + (j)]
+#else
+#define RKB(SS, j) rk_b(SS, j)
+#endif
 template <int G, int SS>
 __device__ __forceinline__ void stage_argument(const double* kcol, const double* y, double* tmp) {
     constexpr int NC = Comp<G>::count;
@@ -94,8 +110,19 @@ __device__ __forceinline__ void stage_argument(const double* kcol, const double*
     for (int i = 0; i < 8; ++i) {
         double acc = y[i];
         if (Comp<G>::stored(i)) {
+#if defined(GRRT_SINCOS_DELTA) && defined(GRRT_FAST_MATH)
+            if (i == 2 && GeomTraits<G>::chart != CH_CART) {
+                // polar angle: the increment sum B k alone (the stage takes sin, cos of theta from it by the addition
+                // theorem, see the stage loop); tmp[2] is not read by the right-hand side in these charts
+                acc = RKB(SS, 0) * kcol[(0 * NC + Comp<G>::slot(i)) * kTraceThreads];
 #pragma unroll
-            for (int j = 0; j < SS; ++j) acc = acc + rk_b(SS, j) * kcol[(j * NC + Comp<G>::slot(i)) * kTraceThreads];
+                for (int j = 1; j < SS; ++j) acc = acc + RKB(SS, j) * kcol[(j * NC + Comp<G>::slot(i)) * kTraceThreads];
+                tmp[i] = acc;
+                continue;
+            }
+#endif
+#pragma unroll
+            for (int j = 0; j < SS; ++j) acc = acc + RKB(SS, j) * kcol[(j * NC + Comp<G>::slot(i)) * kTraceThreads];
         }
         tmp[i] = acc;
     }
@@ -479,6 +506,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
         int finish = -1;       // >= 0: GRRT_STOP_* with which this lane's ray ends
         int ray_error = 0;
         unsigned cand = 0;     // objects that were the nearest hit so far at their turn in Objects::intersects
+        bool geo_pending = false;  // the step just accepted needs the chord / escape tests of the event code
         if (active && S.max_steps <= 1) finish = GRRT_STOP_NONE;  // `for i in 1..max_steps` runs zero times
         bool event = state == ST_IDLE || finish >= 0;
 
@@ -497,9 +525,16 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                     y_new[i] = y[i];
                     acc_e[i] = 0.0;
                 }
+#if defined(GRRT_SINCOS_DELTA) && defined(GRRT_FAST_MATH)
+                double sin0 = 0.0, cos0 = 1.0;
+#endif
                 double* const kcol = s_k + tid;  // this lane's column of the [stage][component][thread] k store
                 double* kst = kcol;
+#ifdef GRRT_UNROLL_STAGES
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
                 for (int s = 0; s < 6; ++s) {
                     double tmp[8];
                     switch (s) {
@@ -514,8 +549,36 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                         default: stage_argument<G, 5>(kcol, y, tmp); break;
                     }
                     double d[8];
+#if defined(GRRT_SINCOS_DELTA) && defined(GRRT_FAST_MATH)
+                    if (GeomTraits<G>::chart != CH_CART) {
+                        // sin, cos of the stage's polar angle theta + delta from those of the state's theta (computed
+                        // once per attempt) and a short polynomial in the small increment delta = sum B k; 99.9 % of
+                        // all increments are below 1/8, larger ones take the full routine
+                        double st, ct;
+                        if (s == 0) {
+                            sincos_pi2(y[2], &sin0, &cos0);
+                            st = sin0;
+                            ct = cos0;
+                        } else {
+                            const double delta = tmp[2];
+                            if (fabs(delta) <= 0.125) {
+                                double sd, cd;
+                                sincos_small(delta, &sd, &cd);
+                                st = fma(sin0, cd, cos0 * sd);
+                                ct = fma(cos0, cd, -(sin0 * sd));
+                            } else {
+                                sincos_pi2(y[2] + delta, &st, &ct);
+                            }
+                        }
+                        geodesic_rhs_trig<G>(S, C, tmp, st, ct, d);
+                    } else
+#endif
                     geodesic_rhs<G>(S, C, tmp, d);
+#if defined(GRRT_UNROLL_STAGES) && !defined(GRRT_FAST_MATH)
+                    const double ch = rk_ch(s), ct = rk_ct(s);
+#else
                     const double ch = c_rk_ch[s], ct = c_rk_ct[s];
+#endif
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         if (Comp<G>::on(i)) {
@@ -524,7 +587,11 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
 #ifdef GRRT_FAST_MATH
                             // CH2 = CT2 = 0 (runge_kutta.rs:43-55): the exact build adds the zeros; skipping them is worth
                             // 3 % for Schwarzschild (C1 382 -> 370 ms) but costs KerrBL 7 % (register allocation at 96)
+#ifdef GRRT_UNROLL_STAGES
+                            if (s != 1) {
+#else
                             if (G == GRRT_GEOM_KERR_BL || s != 1) {
+#endif
                                 y_new[i] = y_new[i] + ch * k;
                                 acc_e[i] = acc_e[i] + ct * k;
                             }
@@ -589,58 +656,70 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                     h = (err / S.epsilon < 1e-5) ? rclamp(h_cur * kHGrowthCap, kHMin, kHMax) : h_proposed;
 #endif
                 }
-                // ---------------- accepted step: chord tests against the objects, stop tests ----------------
+                // ---------------- accepted step: cheap stop tests; chords that may touch something become events ----------------
                 if (accepted) {
                     // far from every object and from the celestial sphere the chord needs no Cartesian end points and
-                    // the previous state (only read when a hit is shaded) is not kept
+                    // the previous state (only read when a hit is shaded) is not kept; otherwise the step is handed to
+                    // the event code below (chord tests, escape test), which keeps the attempt loop short
                     const bool need_geo = segment_needs_cartesian<G>(S, y[1], y[2], y_new[1], y_new[2]);
-                    V3 prev_cart = v3(0.0, 0.0, 0.0);
                     if (need_geo) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) s_yprev[i * kTraceThreads + tid] = y[i];
-                        prev_cart = R.prev_valid ? v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z)) : position_cartesian<G>(S, y);
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) y[i] = y_new[i];
                     ++R.step;
                     R.retries = 0;
                     h_cur = rclamp(h, kHMin, kHMax);
-                    int st;
-                    if (need_geo) {
-                        const V3 cart = position_cartesian<G>(S, y);
-                        // geometric half of Objects::intersects (objects.rs:65-120): which objects become the nearest
-                        // hit when their turn comes; they are shaded, in this order, outside the loop
-                        double shortest = 1.7976931348623157e308;
-                        for (int k = 0; k < S.n_objects; ++k) {
-                            const DObject& o = S.obj[k];
-                            Hit hcur;
-                            bool hit;
-                            if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
-                            else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
-                            else hit = HAS_VOL ? vol_intersects(o, prev_cart, cart, hcur) : false;  // no such object without HAS_VOL
-                            if (!hit) continue;
-                            const double distance = norm3(hcur.point - prev_cart);
-                            if (!(distance < shortest)) continue;
-                            shortest = distance;
-                            cand |= 1u << k;
-                        }
-                        CTX(CX_PREV_X) = cart.x;
-                        CTX(CX_PREV_Y) = cart.y;
-                        CTX(CX_PREV_Z) = cart.z;
-                        R.prev_valid = 1;
-                        st = should_stop<G>(S, y, cart, R.step);
-                    } else {
+                    geo_pending = need_geo;
+                    if (!need_geo) {
                         R.prev_valid = 0;
-                        st = should_stop_inside<G>(S, y, R.step);
+                        const int st = should_stop_inside<G>(S, y, R.step);
+                        if (st != GRRT_STOP_NONE) finish = st;
+                        else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
                     }
-                    if (st != GRRT_STOP_NONE) finish = st;
-                    else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
                 }
-                event = cand != 0u || finish >= 0;
+                event = geo_pending || finish >= 0;
             }
         }
 
         // ================= events =================
+        // ---------------- accepted steps whose chord may touch an object or the celestial sphere ----------------
+        V3 prev_cart = v3(0.0, 0.0, 0.0), cart = v3(0.0, 0.0, 0.0);
+        if (geo_pending) {
+            if (R.prev_valid) {
+                prev_cart = v3(CTX(CX_PREV_X), CTX(CX_PREV_Y), CTX(CX_PREV_Z));
+            } else {
+                double yp[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i * kTraceThreads + tid];
+                prev_cart = position_cartesian<G>(S, yp);
+            }
+            cart = position_cartesian<G>(S, y);
+            // geometric half of Objects::intersects (objects.rs:65-120): which objects become the nearest
+            // hit when their turn comes; they are shaded, in this order, below
+            double shortest = 1.7976931348623157e308;
+            for (int k = 0; k < S.n_objects; ++k) {
+                const DObject& o = S.obj[k];
+                Hit hcur;
+                bool hit;
+                if (o.kind == GRRT_OBJ_SPHERE) hit = sphere_intersects(o, prev_cart, cart, hcur);
+                else if (o.kind == GRRT_OBJ_DISC) hit = disc_intersects(o, prev_cart, cart, hcur);
+                else hit = HAS_VOL ? vol_intersects(o, prev_cart, cart, hcur) : false;  // no such object without HAS_VOL
+                if (!hit) continue;
+                const double distance = norm3(hcur.point - prev_cart);
+                if (!(distance < shortest)) continue;
+                shortest = distance;
+                cand |= 1u << k;
+            }
+            CTX(CX_PREV_X) = cart.x;
+            CTX(CX_PREV_Y) = cart.y;
+            CTX(CX_PREV_Z) = cart.z;
+            R.prev_valid = 1;
+            const int st = should_stop<G>(S, y, cart, R.step);
+            if (st != GRRT_STOP_NONE) finish = st;
+            else if (R.step >= S.max_steps - 1) finish = GRRT_STOP_NONE;  // budget exhausted (integrator.rs:173)
+        }
         auto push_hit = [&](const Cie& hit_color) {
             if (R.n_hits < kMaxHits) {
                 hits[R.n_hits++] = hit_color;
@@ -657,9 +736,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
             double yp[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) yp[i] = s_yprev[i * kTraceThreads + tid];
-            // the same two end points the loop tested (position_cartesian is a pure function of the state)
-            const V3 prev_cart = position_cartesian<G>(S, yp);
-            const V3 cart = position_cartesian<G>(S, y);
+            // prev_cart / cart: the two end points the chord tests above used
             int best_k = -1;
             double best_temperature = 0.0, best_redshift = 0.0;
             Hit best;
