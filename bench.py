@@ -195,7 +195,6 @@ def main():
     ap.add_argument("--width", type=int, default=None, help="override the workload's frame size (not a bench value)")
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kerr-analytic", action="store_true", help="closed-form Kerr-Schild gradient instead of the reference's finite difference")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     wl["opts"] = dict(wl["opts"])
@@ -229,8 +228,6 @@ def main():
 
     opts = abi.default_cli_opts(**wl["opts"])
     scene = api.HostScene(os.path.join(ROOT, wl["toml"]), opts, ROOT)
-    if args.kerr_analytic:
-        scene.c.kerr_rhs_mode = abi.KERR_RHS_ANALYTIC
     sc = scene.c
     W, H = int(sc.camera.cols), int(sc.camera.rows)
     ctx = api.Context(local_rank)
@@ -280,9 +277,7 @@ def main():
     rays_per_step = counts["rays_base"] + counts["rays_supersample"]
     secs = ms * 1e-3
     mrays = rays_per_step * args.steps / secs / 1e6
-    flops = algorithmic_flops(sc.geometry.kind if not args.kerr_analytic else 3, attempts, accepted, samples)
-    if args.kerr_analytic and sc.geometry.kind == abi.GEOM_KERR:
-        flops = attempts * 1580 + accepted * 230 + samples * FLOPS_SAMPLE
+    flops = algorithmic_flops(sc.geometry.kind, attempts, accepted, samples)
 
     # per-kernel time of the dominant kernel (trace_kernel): separate timed pass with events around each launch
     kern_ms, kern_flops = None, None
@@ -310,8 +305,6 @@ def main():
         n_launch = 1 + (1 if n_sel else 0)
         kern_ms = (e0.elapsed_time(e1) + ss_ms) / n_launch
         kern_flops = algorithmic_flops(sc.geometry.kind, tot_cnt[0], tot_cnt[1], tot_cnt[2]) / n_launch
-        if args.kerr_analytic and sc.geometry.kind == abi.GEOM_KERR:
-            kern_flops = (tot_cnt[0] * 1580 + tot_cnt[1] * 230 + tot_cnt[2] * FLOPS_SAMPLE) / n_launch
 
     # end to end through the C ABI with host buffers (grrt_render: upload scene, trace, read back)
     e2e = None

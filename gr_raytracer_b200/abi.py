@@ -21,7 +21,7 @@ OBJ_SPHERE, OBJ_DISC, OBJ_VOLUMETRIC_DISC = range(3)
 TEMP_CONSTANT, TEMP_LUT = range(2)
 TONEMAP_REINHARD, TONEMAP_GLOBAL_LINEAR = range(2)
 CAMVEL_STATIC, CAMVEL_ZAMO, CAMVEL_EXPLICIT = range(3)
-KERR_RHS_REFERENCE_FD, KERR_RHS_ANALYTIC = range(2)
+KERR_RHS_REFERENCE_FD = 0
 
 OK = 0
 ERR_INVALID_ARGUMENT = -1

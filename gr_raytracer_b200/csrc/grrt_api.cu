@@ -398,6 +398,8 @@ int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) 
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (sc->n_objects > GRRT_MAX_OBJECTS) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "too many objects");
     if (sc->camera.rows <= 0 || sc->camera.cols <= 0) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "camera has no pixels");
+    if (sc->kerr_rhs_mode != GRRT_KERR_RHS_REFERENCE_FD)
+        return fail(ctx, GRRT_ERR_INVALID_CONFIGURATION, "kerr_rhs_mode: only the reference's finite-difference right-hand side exists");
     GrrtDeviceScene* ds = new GrrtDeviceScene();
     auto bail = [&](int rc) {
         grrt_scene_free(ctx, ds);

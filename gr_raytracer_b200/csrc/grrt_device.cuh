@@ -473,39 +473,7 @@ GD void geodesic_rhs_trig(const DScene& S, const RayConst& C, const double* y, d
         double xdot[4];
         mat4_vec(gc, p, xdot);
         double acc[3];
-        if (S.kerr_mode == GRRT_KERR_RHS_ANALYTIC) {
-            // closed-form gradient of g = eta + f k k:  pdot_i = 1/2 d_i g_ab xdot^a xdot^b
-            double rho2 = x * x + yy * yy + z * z;
-            double a = S.a;
-            double w = rho2 - a * a;
-            double s = sqrt(w * w + 4.0 * a * a * z * z);
-            double r2 = 0.5 * (w + s);
-            double r = sqrt(r2);
-            double pos3[3] = {x, yy, z};
-            double den = r2 * r2 + a * a * z * z;
-            double num = r2 * r * S.radius;
-            double f = num / den;
-            double q = r2 + a * a;
-            double nx = r * x + a * yy, ny = r * yy - a * x;
-            double kx = nx / q, ky = ny / q, kz = z / r;
-            double kxd = xdot[0] + kx * xdot[1] + ky * xdot[2] + kz * xdot[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double dr2 = pos3[i] + (w * pos3[i] + (i == 2 ? 2.0 * a * a * z : 0.0)) / s;
-                double dr = dr2 / (2.0 * r);
-                double dnum = 3.0 * r2 * dr * S.radius;
-                double dden = 4.0 * r2 * r * dr + (i == 2 ? 2.0 * a * a * z : 0.0);
-                double df = (dnum * den - num * dden) / (den * den);
-                double dq = 2.0 * r * dr;
-                double dnx = dr * x + (i == 0 ? r : 0.0) + (i == 1 ? a : 0.0);
-                double dny = dr * yy + (i == 1 ? r : 0.0) - (i == 0 ? a : 0.0);
-                double dkx = (dnx * q - nx * dq) / (q * q);
-                double dky = (dny * q - ny * dq) / (q * q);
-                double dkz = ((i == 2 ? 1.0 : 0.0) * r - z * dr) / r2;
-                double dkxd = dkx * xdot[1] + dky * xdot[2] + dkz * xdot[3];
-                acc[i] = 0.5 * (df * kxd * kxd + 2.0 * f * kxd * dkxd);
-            }
-        } else {
+        {
             acc[0] = acc[1] = acc[2] = 0.0;
             // the three axes run as a real loop: one copy of the ~700-instruction body instead of three keeps the
             // stage inside the instruction cache (the unrolled version stalled 1.56 cycles per issue on fetch)

@@ -55,6 +55,29 @@ bool ends_with(const std::string& s, const char* suf) {
     return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
 }
 
+// --output-pattern holds exactly one conversion of the form %d or %0Nd (N = 1..9), which is replaced by the frame number;
+// "%%" is a literal per cent sign.  The pattern never reaches printf.
+std::string frame_file_name(const std::string& pattern, long long frame) {
+    std::string out;
+    int conversions = 0;
+    for (size_t i = 0; i < pattern.size(); ++i) {
+        if (pattern[i] != '%') { out += pattern[i]; continue; }
+        if (i + 1 < pattern.size() && pattern[i + 1] == '%') { out += '%'; ++i; continue; }
+        size_t j = i + 1;
+        int width = 0;
+        bool zero = false;
+        if (j < pattern.size() && pattern[j] == '0') { zero = true; ++j; }
+        if (j < pattern.size() && pattern[j] >= '1' && pattern[j] <= '9') { width = pattern[j] - '0'; ++j; }
+        if (j >= pattern.size() || pattern[j] != 'd' || (zero && width == 0) || ++conversions > 1)
+            die("invalid value '" + pattern + "' for '--output-pattern': expected one %d or %0Nd conversion");
+        std::string num = std::to_string(frame);
+        if ((int)num.size() < width) num = std::string((size_t)width - num.size(), zero ? '0' : ' ') + num;
+        out += num;
+        i = j;
+    }
+    if (conversions != 1) die("invalid value '" + pattern + "' for '--output-pattern': expected one %d or %0Nd conversion");
+    return out;
+}
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -244,8 +267,7 @@ int main(int argc, char** argv) {
             device_ms += st.device_ms_total;
             std::vector<uint8_t>& buf = rgb[done & 1];
             if (grrt_tonemap(ctx, xyza.data(), n, opts.tone_mapping, 1.0, buf.data())) die(grrt_last_error(ctx));
-            char name[4096];
-            std::snprintf(name, sizeof name, output_pattern.c_str(), (int)k);
+            const std::string name = frame_file_name(output_pattern, k);
             if (writer.joinable()) writer.join();  // frame k-1 was encoding while this one rendered
             if (!write_error.empty()) die(write_error);
             std::string path = name;

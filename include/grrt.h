@@ -18,7 +18,11 @@
  * device memory.  Errors: integer return codes (0 = ok, <0 = GrrtStatus), no exceptions
  * cross the boundary; per-ray failures are not API errors, they reproduce the
  * reference's "log and keep the default pixel" (raytracer.rs:230-239) and are counted
- * in GrrtStats.  One in-flight call per GrrtCtx.
+ * in GrrtStats.  A GrrtCtx is NOT re-entrant: one in-flight call per context.  That includes
+ * the *_device entry points that take a caller stream -- they share per-context scratch (the
+ * work-queue counter, the sort / select temporary storage, the tone-map maximum), so all
+ * calls on one context must be issued from one thread at a time and onto one stream (or be
+ * ordered by the caller with events).  Use one GrrtCtx per concurrent stream.
  */
 #ifndef GRRT_H
 #define GRRT_H
@@ -69,11 +73,9 @@ enum { GRRT_TEMP_CONSTANT = 0, GRRT_TEMP_LUT = 1 };
 enum { GRRT_TONEMAP_REINHARD = 0, GRRT_TONEMAP_GLOBAL_LINEAR = 1 };
 enum { GRRT_CAMVEL_STATIC = 0, GRRT_CAMVEL_ZAMO = 1, GRRT_CAMVEL_EXPLICIT = 2 };
 
-/* Kerr-Schild right-hand-side evaluation mode (GrrtScene.kerr_rhs_mode) */
-enum {
-    GRRT_KERR_RHS_REFERENCE_FD = 0, /* central-difference metric derivative, as kerr.rs:162-186 */
-    GRRT_KERR_RHS_ANALYTIC = 1      /* closed-form derivative of f k k: faster, NOT bit-compatible */
-};
+/* GrrtScene.kerr_rhs_mode: the Kerr-Schild right-hand side differentiates the metric by central differences exactly as
+ * kerr.rs:162-186 does (the only mode; grrt_render / grrt_scene_upload reject any other value). */
+enum { GRRT_KERR_RHS_REFERENCE_FD = 0 };
 
 typedef enum {
     GRRT_OK = 0,
@@ -193,7 +195,7 @@ typedef struct {
     GrrtTexture celestial;
     double celestial_temperature;
     uint32_t n_objects;
-    int32_t kerr_rhs_mode;         /* GRRT_KERR_RHS_* (only read for GRRT_GEOM_KERR) */
+    int32_t kerr_rhs_mode;         /* must be GRRT_KERR_RHS_REFERENCE_FD (0) */
     GrrtObject objects[GRRT_MAX_OBJECTS];
     /* BlackBodyMapper LUT (texture.rs:121-138), shared by every BlackBody texture */
     uint32_t bb_lut_n;

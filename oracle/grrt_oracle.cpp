@@ -316,43 +316,6 @@ M4 ks_d_metric_cov_fd(double radius, double a, int index, double x, double y, do
         for (int j = 0; j < 4; ++j) d.m[i][j] = (mp.m[i][j] - mm.m[i][j]) / (2.0 * h);
     return d;
 }
-// Optional non-reference mode (GRRT_KERR_RHS_ANALYTIC): closed-form d g_{ab}/dx^i of
-// g = eta + f k k.  Only used to cross-check the device's analytic mode.
-void ks_analytic_grad(double radius, double a, double x, double y, double z, double f_out[1],
-                      double k_out[4], double df[3], double dk[4][3]) {
-    double rho2 = x * x + y * y + z * z;
-    double w = rho2 - a * a;
-    double s = std::sqrt(w * w + 4.0 * a * a * z * z);
-    double r2 = 0.5 * (w + s);
-    double r = std::sqrt(r2);
-    // d(r2)/dx_i
-    double dr2[3] = {x + w * x / s, y + w * y / s, z + (w * z + 2.0 * a * a * z) / s};
-    double dr[3] = {dr2[0] / (2.0 * r), dr2[1] / (2.0 * r), dr2[2] / (2.0 * r)};
-    double den = r2 * r2 + a * a * z * z;
-    double num = r2 * r * radius;
-    double f = num / den;
-    for (int i = 0; i < 3; ++i) {
-        double dnum = 3.0 * r2 * dr[i] * radius;
-        double dden = 4.0 * r2 * r * dr[i] + (i == 2 ? 2.0 * a * a * z : 0.0);
-        df[i] = (dnum * den - num * dden) / (den * den);
-    }
-    double q = r2 + a * a;
-    double kx = (r * x + a * y) / q, ky = (r * y - a * x) / q, kz = z / r;
-    for (int i = 0; i < 3; ++i) {
-        double dq = 2.0 * r * dr[i];
-        double dnx = dr[i] * x + (i == 0 ? r : 0.0) + (i == 1 ? a : 0.0);
-        double dny = dr[i] * y + (i == 1 ? r : 0.0) - (i == 0 ? a : 0.0);
-        dk[0][i] = 0.0;
-        dk[1][i] = (dnx * q - (r * x + a * y) * dq) / (q * q);
-        dk[2][i] = (dny * q - (r * y - a * x) * dq) / (q * q);
-        dk[3][i] = ((i == 2 ? 1.0 : 0.0) * r - z * dr[i]) / r2;
-    }
-    f_out[0] = f;
-    k_out[0] = 1.0;
-    k_out[1] = kx;
-    k_out[2] = ky;
-    k_out[3] = kz;
-}
 
 // ---------------------------------------------------------------------------------------
 // Boyer-Lindquist pieces (geometry/kerr_bl.rs:62-118, 253-272)
@@ -912,17 +875,7 @@ Y8 geodesic(const Solver& s, const Y8& y) {
             M4 gc = ks_metric_contravariant(g.radius, g.a, x, yy, z);
             V4 xdot = mul(gc, p);
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            if (g.kerr_mode == GRRT_KERR_RHS_ANALYTIC) {
-                // -1/2 d_i g^{ab} p_a p_b = +1/2 d_i g_{ab} xdot^a xdot^b with
-                // d_i g_{ab} = d_i f k_a k_b + f (d_i k_a k_b + k_a d_i k_b)
-                double f[1], k[4], df[3], dk[4][3];
-                ks_analytic_grad(g.radius, g.a, x, yy, z, f, k, df, dk);
-                double kx = k[0] * xdot[0] + k[1] * xdot[1] + k[2] * xdot[2] + k[3] * xdot[3];
-                for (int i = 0; i < 3; ++i) {
-                    double dkx = dk[1][i] * xdot[1] + dk[2][i] * xdot[2] + dk[3][i] * xdot[3];
-                    acc[i + 1] = 0.5 * (df[i] * kx * kx + 2.0 * f[0] * kx * dkx);
-                }
-            } else {
+            {
                 for (int idx = 1; idx <= 3; ++idx) {
                     M4 dcov = ks_d_metric_cov_fd(g.radius, g.a, idx, x, yy, z);
                     M4 t = mul(mul(gc, dcov), gc);  // kerr.rs:149-159

@@ -1,6 +1,7 @@
 """torchrun --nproc-per-node N tools/mgpu_check.py: the N-rank frame must equal the single-GPU grrt_render frame bit for bit."""
 import os, sys
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 import numpy as np, torch, torch.distributed as dist
 from gr_raytracer_b200 import api
 from gr_raytracer_b200.renderer import DeviceEngine, FrameRenderer

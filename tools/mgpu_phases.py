@@ -1,6 +1,7 @@
 """torchrun --nproc-per-node N tools/mgpu_phases.py: per-rank phase times of the sharded C2 frame."""
 import os, sys
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 import torch, torch.distributed as dist
 from gr_raytracer_b200 import api
 from gr_raytracer_b200.renderer import DeviceEngine, FrameRenderer
