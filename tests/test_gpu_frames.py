@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from gr_raytracer_b200 import api
-from helpers import ROOT, CONFIGS, config_opts
+from oracle import scene as osc
+from helpers import ROOT, CONFIGS, config_opts, rel_err_xyz
 
 pytestmark = pytest.mark.gpu
 EXE = os.path.join(ROOT, "gr_raytracer_b200", "grrt")
@@ -38,6 +39,16 @@ def test_resident_scene_with_replaced_camera_equals_fresh_scene(name):
                 assert np.array_equal(got[key], want[key]), (name, pos, key)
             assert got["stats"]["pixels_supersampled"] == want["stats"]["pixels_supersampled"]
             fresh.close()
+            # ... and the moved camera against the ORACLE's frame for that camera (not only device against device)
+            ora = osc.render(osc.scene_from_toml(toml, fresh_opts, ROOT))
+            rel = rel_err_xyz(got["xyza"], ora["xyza"])
+            black = np.max(np.abs(ora["xyza"][..., :3]), axis=-1) == 0.0
+            rel = np.where(black, np.max(np.abs(got["xyza"][..., :3]), axis=-1), rel)
+            good = (rel <= 1e-4) & (got["stop"] == ora["stop"]) & (got["ray_class"] == ora["ray_class"])
+            print(f"[frames] {name} camera {pos} {angles}: {100 * good.mean():.2f} % of the resident-scene frame within 1e-4 of the oracle")
+            assert good.mean() >= 0.999, (name, pos)
+            assert (got["steps"] != ora["steps"]).mean() <= 0.01   # the FMA build may flip an accept / reject on a few rays
+            assert got["stats"]["pixels_supersampled"] == ora["stats"]["pixels_supersampled"]
     finally:
         ctx.free_scene(ds)
         resident.close()

@@ -50,7 +50,7 @@ def rel_err(a, b):
     return np.where(scale > 0, err / np.maximum(scale, 1e-300), err)
 
 
-def run(name, n_samples=300, n_long=30, width=None, height=None, seed=2026, ctx=None, verbose=True):
+def run(name, n_samples=300, n_long=30, width=None, height=None, seed=2026, ctx=None, verbose=True, adaptive=True):
     from gr_raytracer_b200 import abi, api
     from oracle import scene as osc
     from helpers import CONFIGS, config_opts
@@ -61,7 +61,10 @@ def run(name, n_samples=300, n_long=30, width=None, height=None, seed=2026, ctx=
         kw["height"] = height
     opts = config_opts(name, **kw)
     toml = os.path.join(ROOT, CONFIGS[name]["toml"])
-    scene = api.HostScene(toml, opts, ROOT)
+    is_text = False
+    if not adaptive:   # the 1-spp pass only
+        toml, is_text = open(toml).read() + "\n[adaptive_sampling]\nenabled = false\n", True
+    scene = api.HostScene(toml, opts, ROOT, is_text=is_text)
     own = ctx is None
     if own:
         ctx = api.Context(0)
@@ -94,7 +97,7 @@ def run(name, n_samples=300, n_long=30, width=None, height=None, seed=2026, ctx=
         if steps[p] <= 100000 or name not in ("C3", "C4"):   # long rays only through --long (CPU time)
             pids.add(p)
     pids = np.array(sorted(pids), dtype=np.int64)
-    oscene = osc.scene_from_toml(toml, opts, ROOT)
+    oscene = osc.scene_from_toml(toml, opts, ROOT, is_text=is_text)
     spa = int(oscene.c.adaptive.samples_per_axis) if oscene.c.adaptive.enabled else 0
     t0 = time.perf_counter()
     o_xyza, o_cls, o_stop, o_steps = oracle_pixels(osc, oscene, W, H, pids, 0)
@@ -121,7 +124,7 @@ def run(name, n_samples=300, n_long=30, width=None, height=None, seed=2026, ctx=
             err[idx] = e2
     bad = np.flatnonzero(~ok)
     res = {
-        "config": name, "width": W, "height": H, "wall_s": wall, "device_ms_total": st["device_ms_total"],
+        "config": name, "adaptive": bool(adaptive), "width": W, "height": H, "wall_s": wall, "device_ms_total": st["device_ms_total"],
         "device_ms_base": st["device_ms_base"], "device_ms_supersample": st["device_ms_supersample"],
         "rays_base": st["rays_base"], "rays_supersample": st["rays_supersample"], "pixels_supersampled": st["pixels_supersampled"],
         "accepted_steps": st["accepted_steps"], "attempts": st["attempts"], "raymarch_samples": st["raymarch_samples"],
@@ -161,8 +164,9 @@ def main():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--out", default=None)
     ap.add_argument("--save-steps", default=None, help="write the per-pixel step counts and stop reasons (npz)")
+    ap.add_argument("--base-only", action="store_true", help="1-spp pass only (adaptive supersampling off)")
     a = ap.parse_args()
-    res, dev = run(a.config, a.samples, a.long, a.width, a.height)
+    res, dev = run(a.config, a.samples, a.long, a.width, a.height, adaptive=not a.base_only)
     if a.out:
         os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
         with open(a.out, "w") as f:
