@@ -60,8 +60,12 @@ def lib():
                                        C.POINTER(abi.GrrtStats)]
     L.grrt_trace_items_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp]
-    L.grrt_trace_items_device_peers.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                                C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, vp]
+    L.grrt_trace_items_device_peers.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                                C.POINTER(vp), vp, vp]
+    L.grrt_order_by_cost_device.argtypes = [vp, vp, C.c_uint32, vp, vp, vp]
+    L.grrt_init_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+    L.grrt_device_count.argtypes = [vp]
     L.grrt_ipc_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]
     L.grrt_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.grrt_ipc_close.argtypes = [vp, vp]
@@ -170,11 +174,22 @@ class Context:
     """One GrrtCtx bound to one CUDA device."""
 
     def __init__(self, device=0):
+        """`device`: a CUDA device ordinal, or a sequence of ordinals for one multi-device context (grrt_init_multi):
+        render() then shards every frame over those GPUs inside the library."""
         self._h = C.c_void_p()
-        rc = lib().grrt_init(device, C.byref(self._h))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = lib().grrt_init_multi(len(device), ids, C.byref(self._h))
+            self.device = int(device[0]) if len(device) else 0
+        else:
+            rc = lib().grrt_init(device, C.byref(self._h))
+            self.device = device
         if rc:
             raise GrrtError(rc, "grrt_init failed: no usable sm_100 CUDA device (this library has no CPU fallback)")
-        self.device = device
+
+    @property
+    def device_count(self):
+        return int(lib().grrt_device_count(self._h))
 
     def _check(self, rc):
         if rc < 0:
@@ -304,14 +319,21 @@ class Context:
                                                          spa, d_xyza, d_class, d_stop, d_steps, d_counters, stream))
 
     def trace_items_device_peers(self, dscene, d_items, n_items, rect, spa, xyza_peers, class_peers, stop_peers,
-                                 d_counters=None, stream=None):
-        """grrt_trace_items_device_peers: results go at their pixel id into every peer's frame buffers."""
+                                 d_counters=None, stream=None, steps_peers=None, item_offset=0, item_stride=1):
+        """grrt_trace_items_device_peers: results go at their pixel id into every peer's frame buffers; item i is
+        d_items[item_offset + i * item_stride]."""
         fr, fc, tr, tc = rect
         n = len(xyza_peers)
         arr = lambda ptrs: (C.c_void_p * n)(*[int(p) for p in ptrs])
-        return self._check(lib().grrt_trace_items_device_peers(self._h, dscene, d_items, n_items, fr, fc, tr, tc, spa, n,
+        return self._check(lib().grrt_trace_items_device_peers(self._h, dscene, d_items, item_offset, item_stride, n_items,
+                                                               fr, fc, tr, tc, spa, n,
                                                                arr(xyza_peers), arr(class_peers), arr(stop_peers),
+                                                               arr(steps_peers) if steps_peers else None,
                                                                d_counters, stream))
+
+    def order_by_cost_device(self, d_selected, n_selected, d_steps, d_ordered, stream=None):
+        """grrt_order_by_cost_device: flagged pixel ids by descending base-pass step count (stable)."""
+        return self._check(lib().grrt_order_by_cost_device(self._h, d_selected, n_selected, d_steps, d_ordered, stream))
 
     # -- frame buffers shared between the processes of one box (cudaIpc) ------------------------------
     def ipc_alloc(self, nbytes):

@@ -29,6 +29,13 @@ struct GrrtCtx {
     size_t cub_temp_bytes = 0;
     unsigned long long launches = 0;  // kernels of this library launched so far (bench.py's gpu_launches)
     bool use_fma = true;              // smooth geometries: FMA-contracted kernels (GRRT_FMA=0 or grrt_set_option to disable)
+    // grrt_init_multi: the context of device_ids[0] owns one member context per further device; frames are sharded
+    // over all of them and assembled in this (the primary) device's memory by peer stores
+    std::vector<GrrtCtx*> members;
+    // per-device share of the 8x4-tile round-robin partition of the last frame geometry rendered (multi-device only)
+    uint32_t part_w = 0, part_h = 0;
+    std::vector<uint32_t*> d_part_items;   // [1 + members.size()], each on its own device
+    std::vector<uint64_t> part_counts;
 };
 
 struct GrrtDeviceScene {
@@ -36,6 +43,7 @@ struct GrrtDeviceScene {
     std::vector<void*> allocs;
     GrrtAdaptive adaptive;
     bool has_vol = false;
+    std::vector<GrrtDeviceScene*> replicas;  // multi-device context: the same scene on members[k]'s device
 };
 
 namespace {
@@ -236,9 +244,11 @@ struct PeerFrames {
     double* xyza[GRRT_MAX_PEERS];
 };
 __global__ void grrt_exact_resolve(const double* sub_xyza, const uint8_t* sub_valid, const uint32_t* items,
+                                   unsigned long long item_offset, unsigned long long item_stride,
                                    unsigned long long n_items, unsigned ss, double* xyza, PeerFrames peers) {
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (i >= n_items) return;
+    const unsigned long long pid = items[item_offset + i * item_stride];
     double sx = 0.0, sy = 0.0, sz = 0.0, sa = 0.0;
     unsigned valid = 0;
     for (unsigned k = 0; k < ss; ++k) {
@@ -253,11 +263,11 @@ __global__ void grrt_exact_resolve(const double* sub_xyza, const uint8_t* sub_va
         double inv = 1.0 / (double)valid;
         const double m0 = sx * inv, m1 = sy * inv, m2 = sz * inv, m3 = sa * inv;
         if (peers.n == 0) {
-            double* dst = xyza + 4ull * items[i];
+            double* dst = xyza + 4ull * pid;
             dst[0] = m0; dst[1] = m1; dst[2] = m2; dst[3] = m3;
         } else {
             for (unsigned p = 0; p < peers.n; ++p) {  // the mean goes into every rank's frame
-                double* dst = peers.xyza[p] + 4ull * items[i];
+                double* dst = peers.xyza[p] + 4ull * pid;
                 dst[0] = m0; dst[1] = m1; dst[2] = m2; dst[3] = m3;
             }
         }
@@ -308,7 +318,7 @@ extern "C" {
 
 const char* grrt_version(void) { return "grrt-b200 0.1 (sm_100a)"; }
 
-int grrt_init(int device_id, GrrtCtx** out) {
+static int init_one(int device_id, GrrtCtx** out) {
     if (!out) return GRRT_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     int count = 0;
@@ -346,8 +356,66 @@ int grrt_init(int device_id, GrrtCtx** out) {
     return GRRT_OK;
 }
 
+int grrt_init(int device_id, GrrtCtx** out) { return init_one(device_id, out); }
+
+int grrt_init_multi(int n_devices, const int* device_ids, GrrtCtx** out) {
+    if (!out) return GRRT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (n_devices < 1 || n_devices > GRRT_MAX_PEERS || !device_ids) return GRRT_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (device_ids[i] == device_ids[j]) return GRRT_ERR_INVALID_ARGUMENT;
+    GrrtCtx* primary = nullptr;
+    int rc = init_one(device_ids[0], &primary);
+    if (rc) return rc;
+    for (int i = 1; i < n_devices; ++i) {
+        GrrtCtx* m = nullptr;
+        rc = init_one(device_ids[i], &m);
+        if (rc == GRRT_OK) {
+            // the member's kernels store finished pixels into the primary device's frame over NVLink
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, device_ids[i], device_ids[0]) != cudaSuccess || !can) rc = GRRT_ERR_CUDA;
+        }
+        if (rc == GRRT_OK) {
+            cudaSetDevice(device_ids[i]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[0], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) rc = GRRT_ERR_CUDA;
+        }
+        if (rc == GRRT_OK) {  // frame buffers come from the primary's stream-ordered pool: open it to the member
+            cudaMemPool_t pool;
+            cudaMemAccessDesc desc;
+            std::memset(&desc, 0, sizeof desc);
+            desc.location.type = cudaMemLocationTypeDevice;
+            desc.location.id = device_ids[i];
+            desc.flags = cudaMemAccessFlagsProtReadWrite;
+            if (cudaDeviceGetDefaultMemPool(&pool, device_ids[0]) != cudaSuccess || cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess)
+                rc = GRRT_ERR_CUDA;
+        }
+        if (rc != GRRT_OK) {
+            if (m) grrt_destroy(m);
+            grrt_destroy(primary);
+            return rc;
+        }
+        m->use_fma = primary->use_fma;
+        primary->members.push_back(m);
+    }
+    cudaSetDevice(device_ids[0]);
+    *out = primary;
+    return GRRT_OK;
+}
+
+int grrt_device_count(const GrrtCtx* ctx) { return ctx ? 1 + (int)ctx->members.size() : 0; }
+
 void grrt_destroy(GrrtCtx* ctx) {
     if (!ctx) return;
+    for (size_t k = 0; k < ctx->d_part_items.size(); ++k) {
+        if (!ctx->d_part_items[k]) continue;
+        cudaSetDevice(k == 0 ? ctx->device : ctx->members[k - 1]->device);
+        cudaFree(ctx->d_part_items[k]);
+    }
+    for (GrrtCtx* m : ctx->members) grrt_destroy(m);
+    ctx->members.clear();
     cudaSetDevice(ctx->device);
     if (ctx->d_srgb_lut) cudaFree(ctx->d_srgb_lut);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
@@ -361,12 +429,18 @@ int grrt_set_option(GrrtCtx* ctx, const char* name, int value) {
     if (!ctx || !name) return GRRT_ERR_INVALID_ARGUMENT;
     if (std::strcmp(name, "fma") == 0) {
         ctx->use_fma = value != 0;
+        for (GrrtCtx* m : ctx->members) m->use_fma = ctx->use_fma;
         return GRRT_OK;
     }
     return GRRT_ERR_INVALID_ARGUMENT;
 }
 
-unsigned long long grrt_kernel_launch_count(const GrrtCtx* ctx) { return ctx ? ctx->launches : 0; }
+unsigned long long grrt_kernel_launch_count(const GrrtCtx* ctx) {
+    if (!ctx) return 0;
+    unsigned long long n = ctx->launches;
+    for (const GrrtCtx* m : ctx->members) n += m->launches;
+    return n;
+}
 
 const char* grrt_last_error(const GrrtCtx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
 
@@ -389,10 +463,33 @@ int grrt_scene_set_camera(GrrtCtx* ctx, GrrtDeviceScene* ds, const GrrtCamera* c
     if (!ctx || !ds || !camera) return GRRT_ERR_INVALID_ARGUMENT;
     if (camera->rows <= 0 || camera->cols <= 0) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "camera has no pixels");
     set_camera(ds->s, *camera);  // the scene block travels as a kernel argument: nothing to copy to the device
+    for (GrrtDeviceScene* r : ds->replicas) set_camera(r->s, *camera);
     return GRRT_OK;
 }
 
+static int scene_upload_one(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out);
+
 int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) {
+    if (!ctx || !sc || !out) return GRRT_ERR_INVALID_ARGUMENT;
+    int rc = scene_upload_one(ctx, sc, out);
+    if (rc) return rc;
+    for (GrrtCtx* m : ctx->members) {  // the same scene on every device of a multi-device context
+        GrrtDeviceScene* r = nullptr;
+        rc = scene_upload_one(m, sc, &r);
+        if (rc) {
+            ctx->last_error = m->last_error;
+            grrt_scene_free(ctx, *out);
+            *out = nullptr;
+            cudaSetDevice(ctx->device);
+            return rc;
+        }
+        (*out)->replicas.push_back(r);
+    }
+    cudaSetDevice(ctx->device);
+    return GRRT_OK;
+}
+
+static int scene_upload_one(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) {
     if (!ctx || !sc || !out) return GRRT_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -493,6 +590,9 @@ int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) 
 
 void grrt_scene_free(GrrtCtx* ctx, GrrtDeviceScene* ds) {
     if (!ds) return;
+    for (size_t k = 0; k < ds->replicas.size(); ++k)
+        grrt_scene_free(ctx && k < ctx->members.size() ? ctx->members[k] : nullptr, ds->replicas[k]);
+    ds->replicas.clear();
     if (ctx) cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();  // the scene may be in use on a caller's stream
     for (void* p : ds->allocs) cudaFreeAsync(p, ctx ? ctx->stream : nullptr);
@@ -500,18 +600,30 @@ void grrt_scene_free(GrrtCtx* ctx, GrrtDeviceScene* ds) {
 }
 
 namespace {
+struct TraceOpts {   // everything beyond the plain item list of grrt_trace_items_device
+    uint64_t item_offset = 0, item_stride = 1;   // item i of this call is d_items[item_offset + i * item_stride]
+    uint32_t n_peers = 0;                        // > 0: results go at their pixel id into every peer's frame
+    double* const* xyza_peers = nullptr;
+    uint8_t* const* class_peers = nullptr;
+    uint8_t* const* stop_peers = nullptr;
+    uint32_t* const* steps_peers = nullptr;      // nullable, and so is every entry
+};
+
 int trace_items_impl(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_items, uint64_t first_item,
                      uint64_t n_items, uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
                      uint32_t samples_per_axis, double* d_xyza, uint8_t* d_class, uint8_t* d_stop, uint32_t* d_steps,
-                     uint64_t* d_counters, void* cuda_stream, uint32_t n_peers, double* const* xyza_peers,
-                     uint8_t* const* class_peers, uint8_t* const* stop_peers) {
+                     uint64_t* d_counters, void* cuda_stream, const TraceOpts& o) {
     if (to_row < from_row || to_col < from_col) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "empty or inverted section");
+    if (o.item_stride == 0) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "item_stride must be at least 1");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     if (n_items == 0) return GRRT_OK;
+    const uint32_t n_peers = o.n_peers;
     TraceArgs a;
     std::memset(&a, 0, sizeof a);
     a.items = d_items;
+    a.item_offset = o.item_offset;
+    a.item_stride = o.item_stride;
     a.first_item = first_item;
     a.n_items = n_items;
     a.from_row = from_row;
@@ -523,7 +635,7 @@ int trace_items_impl(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_
     PeerFrames pf;
     std::memset(&pf, 0, sizeof pf);
     pf.n = n_peers;
-    for (uint32_t p = 0; p < n_peers; ++p) pf.xyza[p] = xyza_peers[p];
+    for (uint32_t p = 0; p < n_peers; ++p) pf.xyza[p] = o.xyza_peers[p];
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned long long), st));
     if (samples_per_axis == 0) {
         a.spa = 0;
@@ -533,9 +645,10 @@ int trace_items_impl(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_
         a.steps = d_steps;
         a.n_peers = n_peers;
         for (uint32_t p = 0; p < n_peers; ++p) {
-            a.xyza_p[p] = xyza_peers[p];
-            a.cls_p[p] = class_peers[p];
-            a.stop_p[p] = stop_peers[p];
+            a.xyza_p[p] = o.xyza_peers[p];
+            a.cls_p[p] = o.class_peers[p];
+            a.stop_p[p] = o.stop_peers[p];
+            a.steps_p[p] = o.steps_peers ? o.steps_peers[p] : nullptr;
         }
         const bool whole = !d_items && first_item == 0 && n_items == (uint64_t)a.width * a.height;
         if (whole) {  // enumerate 8x4 pixel tiles so that a warp starts on a compact patch of the image
@@ -557,7 +670,7 @@ int trace_items_impl(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_
     CUDA_TRY(ctx, valid.alloc(cap * ss, st));
     for (uint64_t off = 0; off < n_items; off += cap) {
         uint64_t m = std::min<uint64_t>(cap, n_items - off);
-        a.items = d_items + off;
+        a.item_offset = o.item_offset + off * o.item_stride;
         a.n_items = m;
         a.spa = samples_per_axis;
         a.n_units = m * ss;
@@ -566,8 +679,8 @@ int trace_items_impl(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned long long), st));
         int rc = launch_trace(ctx, ds, a, st);
         if (rc) return rc;
-        grrt_exact_resolve<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(sub.as<double>(), valid.as<uint8_t>(),
-                                                                                d_items + off, m, ss, d_xyza, pf);
+        grrt_exact_resolve<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(sub.as<double>(), valid.as<uint8_t>(), d_items,
+                                                                                a.item_offset, a.item_stride, m, ss, d_xyza, pf);
         ++ctx->launches;
         CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -581,24 +694,30 @@ int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint3
                             uint32_t* d_steps, uint64_t* d_counters, void* cuda_stream) {
     if (!ctx || !ds || !d_xyza) return GRRT_ERR_INVALID_ARGUMENT;
     return trace_items_impl(ctx, ds, d_items, first_item, n_items, from_row, from_col, to_row, to_col, samples_per_axis, d_xyza,
-                            d_class, d_stop, d_steps, d_counters, cuda_stream, 0, nullptr, nullptr, nullptr);
+                            d_class, d_stop, d_steps, d_counters, cuda_stream, TraceOpts());
 }
 
-int grrt_trace_items_device_peers(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_items, uint64_t n_items,
-                                  uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
-                                  uint32_t samples_per_axis, uint32_t n_peers, double* const* d_xyza_peers,
-                                  uint8_t* const* d_class_peers, uint8_t* const* d_stop_peers, uint64_t* d_counters,
-                                  void* cuda_stream) {
+int grrt_trace_items_device_peers(GrrtCtx* ctx, const GrrtDeviceScene* ds, const uint32_t* d_items, uint64_t item_offset,
+                                  uint64_t item_stride, uint64_t n_items, uint32_t from_row, uint32_t from_col,
+                                  uint32_t to_row, uint32_t to_col, uint32_t samples_per_axis, uint32_t n_peers,
+                                  double* const* d_xyza_peers, uint8_t* const* d_class_peers, uint8_t* const* d_stop_peers,
+                                  uint32_t* const* d_steps_peers, uint64_t* d_counters, void* cuda_stream) {
     if (!ctx || !ds || !d_items || !d_xyza_peers || !d_class_peers || !d_stop_peers) return GRRT_ERR_INVALID_ARGUMENT;
     if (n_peers == 0 || n_peers > GRRT_MAX_PEERS) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "1..GRRT_MAX_PEERS peers");
     for (uint32_t p = 0; p < n_peers; ++p)
         if (!d_xyza_peers[p] || !d_class_peers[p] || !d_stop_peers[p]) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "null peer buffer");
+    TraceOpts o;
+    o.item_offset = item_offset;
+    o.item_stride = item_stride;
+    o.n_peers = n_peers;
+    o.xyza_peers = d_xyza_peers;
+    o.class_peers = d_class_peers;
+    o.stop_peers = d_stop_peers;
+    o.steps_peers = d_steps_peers;
     return trace_items_impl(ctx, ds, d_items, 0, n_items, from_row, from_col, to_row, to_col, samples_per_axis, d_xyza_peers[0],
-                            nullptr, nullptr, nullptr, d_counters, cuda_stream, n_peers, d_xyza_peers, d_class_peers,
-                            d_stop_peers);
+                            nullptr, nullptr, nullptr, d_counters, cuda_stream, o);
 }
 
-// ---- frame buffers shared between the processes of one box (cudaIpc) -----------------------------------------
 int grrt_ipc_alloc(GrrtCtx* ctx, size_t bytes, void** d_ptr, unsigned char handle_out[64]) {
     if (!ctx || !d_ptr || !handle_out) return GRRT_ERR_INVALID_ARGUMENT;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -734,11 +853,112 @@ int grrt_render(GrrtCtx* ctx, const GrrtScene* scene, uint32_t from_row, uint32_
     return rc;
 }
 
+namespace {
+// ---- supersampling order --------------------------------------------------------------------------------
+// The base pass is the pilot of the second pass: a flagged pixel's 16 sub-sample rays take about as many RKF45 steps
+// as its centre ray did.  The flagged pixels are therefore traced longest first (the work queue then ends on the
+// short rays, not on a straggler) and, on several devices, dealt round-robin in that order so that every device gets
+// the same share of the expensive ones.  The image does not depend on the order: every pixel's mean is taken over
+// its own strata in stratum order.
+__global__ void cost_keys_kernel(const uint32_t* sel, uint32_t n, const uint32_t* steps, uint32_t* keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ~steps[sel[i]];   // ascending ~steps = descending steps; the radix sort is stable
+}
+}  // namespace
+
+int grrt_order_by_cost_device(GrrtCtx* ctx, const uint32_t* d_selected, uint32_t n_selected, const uint32_t* d_steps,
+                              uint32_t* d_ordered, void* cuda_stream) {
+    if (!ctx || !d_selected || !d_steps || !d_ordered) return GRRT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (n_selected == 0) return GRRT_OK;
+    DevBuf k_in, k_out;
+    CUDA_TRY(ctx, k_in.alloc((size_t)n_selected * 4, st));
+    CUDA_TRY(ctx, k_out.alloc((size_t)n_selected * 4, st));
+    cost_keys_kernel<<<(n_selected + 255) / 256, 256, 0, st>>>(d_selected, n_selected, d_steps, k_in.as<uint32_t>());
+    ++ctx->launches;
+    size_t tmp = 0;
+    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in.as<uint32_t>(), k_out.as<uint32_t>(), d_selected, d_ordered,
+                                                  (int)n_selected, 0, 32, st));
+    int rc = ensure_cub_temp(ctx, tmp);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_cub_temp, tmp, k_in.as<uint32_t>(), k_out.as<uint32_t>(), d_selected,
+                                                  d_ordered, (int)n_selected, 0, 32, st));
+    return GRRT_OK;
+}
+
+namespace {
+// 8x4-pixel tiles dealt round-robin to the devices (tile-major, so 32 consecutive work units are one compact patch);
+// the same partition as gr_raytracer_b200/renderer.py:tile_interleaved_items
+int ensure_partition(GrrtCtx* ctx, uint32_t W, uint32_t H) {
+    const size_t N = 1 + ctx->members.size();
+    if (ctx->part_w == W && ctx->part_h == H && ctx->d_part_items.size() == N) return GRRT_OK;
+    for (size_t k = 0; k < ctx->d_part_items.size(); ++k) {
+        if (!ctx->d_part_items[k]) continue;
+        cudaSetDevice(k == 0 ? ctx->device : ctx->members[k - 1]->device);
+        cudaFree(ctx->d_part_items[k]);
+    }
+    ctx->d_part_items.assign(N, nullptr);
+    ctx->part_counts.assign(N, 0);
+    ctx->part_w = ctx->part_h = 0;
+    const uint64_t tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4;
+    std::vector<uint32_t> ids;
+    for (size_t d = 0; d < N; ++d) {
+        ids.clear();
+        for (uint64_t t = d; t < tiles_x * tiles_y; t += N) {
+            const uint64_t ty = t / tiles_x, tx = t % tiles_x;
+            for (uint32_t k = 0; k < 32; ++k) {
+                const uint64_t py = ty * 4 + (k >> 3), px = tx * 8 + (k & 7);
+                if (py < H && px < W) ids.push_back((uint32_t)(py * W + px));
+            }
+        }
+        GrrtCtx* c = d == 0 ? ctx : ctx->members[d - 1];
+        CUDA_TRY(ctx, cudaSetDevice(c->device));
+        ctx->part_counts[d] = ids.size();
+        if (!ids.empty()) {
+            CUDA_TRY(ctx, cudaMalloc(&ctx->d_part_items[d], ids.size() * 4));
+            CUDA_TRY(ctx, cudaMemcpy(ctx->d_part_items[d], ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    ctx->part_w = W;
+    ctx->part_h = H;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return GRRT_OK;
+}
+
+struct EventSet {   // events of one frame, destroyed on scope exit (each on the device it was created on)
+    std::vector<std::pair<int, cudaEvent_t>> ev;
+    ~EventSet() {
+        for (auto& e : ev) {
+            cudaSetDevice(e.first);
+            cudaEventDestroy(e.second);
+        }
+    }
+    cudaError_t make(int device, cudaEvent_t* out, unsigned flags = cudaEventDefault) {
+        cudaError_t e = cudaSetDevice(device);
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreateWithFlags(out, flags);
+        if (e == cudaSuccess) ev.emplace_back(device, *out);
+        return e;
+    }
+};
+}  // namespace
+
+// One frame: 1-spp base pass, adaptive mask, supersampling of the flagged pixels (raytracer.rs:177-193, 257-318), on the
+// device of `ctx` or -- for a grrt_init_multi context -- sharded over all its devices.  Multi-device: every device
+// traces its share of the 8x4 tiles and stores each finished pixel straight into the PRIMARY device's frame (peer
+// stores over NVLink from inside the trace kernel; there is no reduction, hence no collective and no gather pass); the
+// primary derives the mask and the cost order, every device supersamples every N-th flagged pixel of that order --
+// reading the list from the primary's memory -- and stores the means into the primary's frame.  Stream-ordered events
+// separate the passes; the host waits once (for the flagged count), as in the single-device frame.  The result is bit
+// for bit the single-device frame.
 int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_row, uint32_t from_col, uint32_t to_row,
                          uint32_t to_col, double* xyza_out, uint8_t* ray_class_out, uint8_t* stop_reason_out,
                          uint32_t* steps_out, GrrtStats* stats) {
     if (!ctx || !ds || !xyza_out) return GRRT_ERR_INVALID_ARGUMENT;
     if (to_row < from_row || to_col < from_col) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "inverted section");
+    const size_t N = 1 + ctx->members.size();
+    if (ds->replicas.size() != N - 1) return fail(ctx, GRRT_ERR_INVALID_ARGUMENT, "scene was not uploaded through this context");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc = GRRT_OK;
     const uint32_t W = to_col - from_col, H = to_row - from_row;
@@ -749,24 +969,62 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
         if (stats) *stats = st;
         return GRRT_OK;
     }
+    auto dev_ctx = [&](size_t d) { return d == 0 ? ctx : ctx->members[d - 1]; };
+    auto dev_scene = [&](size_t d) { return d == 0 ? ds : ds->replicas[d - 1]; };
+    struct Restore {   // leave the primary device current, whatever happens
+        int device;
+        ~Restore() { cudaSetDevice(device); }
+    } restore{ctx->device};
+    if (N > 1) {
+        rc = ensure_partition(ctx, W, H);
+        if (rc) return rc;
+    }
     cudaStream_t s = ctx->stream;
-    DevBuf xyza, cls, stop, steps, sel, cnt;
+    DevBuf xyza, cls, stop, steps, sel, ordered, cnt;
     CUDA_TRY(ctx, xyza.alloc(n * 32, s));
     CUDA_TRY(ctx, cls.alloc(n, s));
     CUDA_TRY(ctx, stop.alloc(n, s));
     CUDA_TRY(ctx, steps.alloc(n * 4, s));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), s));
+    for (size_t d = 0; d < N; ++d) {
+        GrrtCtx* c = dev_ctx(d);
+        CUDA_TRY(ctx, cudaSetDevice(c->device));
+        CUDA_TRY(ctx, cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    EventSet events;
     cudaEvent_t ev[4];
-    for (auto& e : ev) CUDA_TRY(ctx, cudaEventCreate(&e));
-    struct EvGuard {
-        cudaEvent_t* e;
-        ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); }
-    } evg{ev};
+    for (auto& e : ev) CUDA_TRY(ctx, events.make(ctx->device, &e));
     CUDA_TRY(ctx, cudaEventRecord(ev[0], s));
-    rc = grrt_trace_items_device(ctx, ds, nullptr, 0, n, from_row, from_col, to_row, to_col, 0, xyza.as<double>(),
-                                 cls.as<uint8_t>(), stop.as<uint8_t>(), steps.as<uint32_t>(),
-                                 (uint64_t*)ctx->d_counters, s);
-    if (rc) return rc;
+    // ---- base pass ----
+    if (N == 1) {
+        rc = grrt_trace_items_device(ctx, ds, nullptr, 0, n, from_row, from_col, to_row, to_col, 0, xyza.as<double>(),
+                                     cls.as<uint8_t>(), stop.as<uint8_t>(), steps.as<uint32_t>(),
+                                     (uint64_t*)ctx->d_counters, s);
+        if (rc) return rc;
+    } else {
+        double* px[1] = {xyza.as<double>()};
+        uint8_t* pc[1] = {cls.as<uint8_t>()};
+        uint8_t* ps[1] = {stop.as<uint8_t>()};
+        uint32_t* pt[1] = {steps.as<uint32_t>()};
+        TraceOpts o;
+        o.n_peers = 1;
+        o.xyza_peers = px; o.class_peers = pc; o.stop_peers = ps; o.steps_peers = pt;
+        for (size_t d = 0; d < N; ++d) {
+            GrrtCtx* c = dev_ctx(d);
+            if (d > 0) CUDA_TRY(ctx, cudaStreamWaitEvent(c->stream, ev[0], 0));   // the frame buffers exist from here on
+            rc = trace_items_impl(c, dev_scene(d), ctx->d_part_items[d], 0, ctx->part_counts[d], from_row, from_col, to_row, to_col,
+                                  0, px[0], nullptr, nullptr, nullptr, (uint64_t*)c->d_counters, c->stream, o);
+            if (rc) { if (d > 0) ctx->last_error = c->last_error; return rc; }
+            if (d > 0) {
+                cudaEvent_t done;
+                CUDA_TRY(ctx, events.make(c->device, &done, cudaEventDisableTiming));
+                CUDA_TRY(ctx, cudaEventRecord(done, c->stream));
+                CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(s, done, 0));
+            }
+        }
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    }
     CUDA_TRY(ctx, cudaEventRecord(ev[1], s));
     st.rays_base = n;
     const GrrtAdaptive& ad = ds->adaptive;
@@ -780,22 +1038,55 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
         if (rc) return rc;
         CUDA_TRY(ctx, cudaMemcpyAsync(&n_sel, cnt.p, 4, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(ctx, cudaStreamSynchronize(s));
-        CUDA_TRY(ctx, cudaEventRecord(ev[2], s));
         st.pixels_supersampled = n_sel;
         if (n_sel) {
             if (ad.show_sampling_mask) {
                 fill_mask_color_kernel<<<(n_sel + 255) / 256, 256, 0, s>>>(sel.as<uint32_t>(), n_sel, ad, xyza.as<double>());
                 ++ctx->launches;
                 CUDA_TRY(ctx, cudaGetLastError());
+                CUDA_TRY(ctx, cudaEventRecord(ev[2], s));
             } else {
                 if (ad.samples_per_axis == 0 || ad.samples_per_axis > 4096)
                     return fail(ctx, GRRT_ERR_INVALID_CONFIGURATION, "adaptive_sampling.samples_per_axis must be greater than zero");
-                rc = grrt_trace_items_device(ctx, ds, sel.as<uint32_t>(), 0, n_sel, from_row, from_col, to_row, to_col,
-                                             (uint32_t)ad.samples_per_axis, xyza.as<double>(), nullptr, nullptr, nullptr,
-                                             (uint64_t*)ctx->d_counters, s);
+                const uint32_t spa = (uint32_t)ad.samples_per_axis;
+                CUDA_TRY(ctx, ordered.alloc((size_t)n_sel * 4, s));
+                rc = grrt_order_by_cost_device(ctx, sel.as<uint32_t>(), n_sel, steps.as<uint32_t>(), ordered.as<uint32_t>(), s);
                 if (rc) return rc;
-                st.rays_supersample = (uint64_t)n_sel * ad.samples_per_axis * ad.samples_per_axis;
+                CUDA_TRY(ctx, cudaEventRecord(ev[2], s));
+                if (N == 1) {
+                    rc = grrt_trace_items_device(ctx, ds, ordered.as<uint32_t>(), 0, n_sel, from_row, from_col, to_row, to_col, spa,
+                                                 xyza.as<double>(), nullptr, nullptr, nullptr, (uint64_t*)ctx->d_counters, s);
+                    if (rc) return rc;
+                } else {
+                    double* px[1] = {xyza.as<double>()};
+                    uint8_t* pc[1] = {cls.as<uint8_t>()};
+                    uint8_t* ps[1] = {stop.as<uint8_t>()};
+                    for (size_t d = 0; d < N && d < n_sel; ++d) {
+                        GrrtCtx* c = dev_ctx(d);
+                        TraceOpts o;
+                        o.item_offset = d;
+                        o.item_stride = N;
+                        o.n_peers = 1;
+                        o.xyza_peers = px; o.class_peers = pc; o.stop_peers = ps;
+                        if (d > 0) CUDA_TRY(ctx, cudaStreamWaitEvent(c->stream, ev[2], 0));   // mask and order are final
+                        const uint64_t mine = (n_sel - d + N - 1) / N;
+                        rc = trace_items_impl(c, dev_scene(d), ordered.as<uint32_t>(), 0, mine, from_row, from_col, to_row, to_col,
+                                              spa, px[0], nullptr, nullptr, nullptr, (uint64_t*)c->d_counters, c->stream, o);
+                        if (rc) { if (d > 0) ctx->last_error = c->last_error; return rc; }
+                        if (d > 0) {
+                            cudaEvent_t done;
+                            CUDA_TRY(ctx, events.make(c->device, &done, cudaEventDisableTiming));
+                            CUDA_TRY(ctx, cudaEventRecord(done, c->stream));
+                            CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+                            CUDA_TRY(ctx, cudaStreamWaitEvent(s, done, 0));
+                        }
+                    }
+                    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+                }
+                st.rays_supersample = (uint64_t)n_sel * spa * spa;
             }
+        } else {
+            CUDA_TRY(ctx, cudaEventRecord(ev[2], s));
         }
     }
     CUDA_TRY(ctx, cudaEventRecord(ev[3], s));
@@ -803,15 +1094,23 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
     if (ray_class_out) CUDA_TRY(ctx, cudaMemcpyAsync(ray_class_out, cls.p, n, cudaMemcpyDeviceToHost, s));
     if (stop_reason_out) CUDA_TRY(ctx, cudaMemcpyAsync(stop_reason_out, stop.p, n, cudaMemcpyDeviceToHost, s));
     if (steps_out) CUDA_TRY(ctx, cudaMemcpyAsync(steps_out, steps.p, n * 4, cudaMemcpyDeviceToHost, s));
-    unsigned long long c[16];
-    CUDA_TRY(ctx, cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, s));
+    unsigned long long c[16], total[16];
+    std::memset(total, 0, sizeof total);
+    for (size_t d = 0; d < N; ++d) {   // the primary's stream has waited for every member's kernels
+        GrrtCtx* m = dev_ctx(d);
+        CUDA_TRY(ctx, cudaSetDevice(m->device));
+        CUDA_TRY(ctx, cudaMemcpyAsync(c, m->d_counters, sizeof c, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(m->stream));
+        for (int k = 0; k < 16; ++k) total[k] += c[k];
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    st.attempts = c[CNT_ATTEMPTS];
-    st.accepted_steps = c[CNT_ACCEPTED];
-    st.raymarch_samples = c[CNT_SAMPLES];
-    st.ray_errors = c[CNT_ERRORS];
-    st.hit_stack_overflows = c[CNT_OVERFLOW];
-    for (int k = 0; k < 6; ++k) st.stop_histogram[k] = c[CNT_STOP0 + k];
+    st.attempts = total[CNT_ATTEMPTS];
+    st.accepted_steps = total[CNT_ACCEPTED];
+    st.raymarch_samples = total[CNT_SAMPLES];
+    st.ray_errors = total[CNT_ERRORS];
+    st.hit_stack_overflows = total[CNT_OVERFLOW];
+    for (int k = 0; k < 6; ++k) st.stop_histogram[k] = total[CNT_STOP0 + k];
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev[0], ev[1]); st.device_ms_base = ms;
     cudaEventElapsedTime(&ms, ev[1], ev[2]); st.device_ms_mask = ms;

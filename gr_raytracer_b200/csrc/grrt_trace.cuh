@@ -461,7 +461,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                         pid = (unsigned long long)py * A.width + px;
                         item = pid;
                     } else {
-                        pid = A.items ? (unsigned long long)A.items[item] : A.first_item + item;
+                        pid = A.items ? (unsigned long long)A.items[A.item_offset + item * A.item_stride] : A.first_item + item;
                     }
                     if (ok) {
                         const long long row = (long long)(pid / A.width) + A.from_row;
@@ -880,6 +880,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                     dst[0] = result.x; dst[1] = result.y; dst[2] = result.z; dst[3] = result.a;
                     A.cls_p[p][o] = (uint8_t)ray_class;
                     A.stop_p[p][o] = (uint8_t)finish;
+                    if (A.steps_p[p]) A.steps_p[p][o] = (uint32_t)R.step;
                 }
                 if (A.steps) A.steps[o] = (uint32_t)R.step;
             } else if (A.spa == 0) {

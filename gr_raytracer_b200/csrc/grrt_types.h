@@ -71,7 +71,8 @@ enum { CNT_ATTEMPTS = 0, CNT_ACCEPTED = 1, CNT_SAMPLES = 2, CNT_ERRORS = 3, CNT_
        CNT_STOP0 = 8 /* 8..13 */ };
 
 struct TraceArgs {
-    const uint32_t* items;      // nullable: pixel ids (row-major within the rectangle)
+    const uint32_t* items;      // nullable: pixel ids (row-major within the rectangle); item i is items[item_offset + i * item_stride]
+    unsigned long long item_offset, item_stride;   // a rank's share of a list that is dealt round-robin (stride >= 1)
     unsigned long long first_item;
     unsigned long long n_items;
     unsigned long long n_units;  // work units handed out by the queue
@@ -92,6 +93,7 @@ struct TraceArgs {
     double* xyza_p[GRRT_MAX_PEERS];
     uint8_t* cls_p[GRRT_MAX_PEERS];
     uint8_t* stop_p[GRRT_MAX_PEERS];
+    uint32_t* steps_p[GRRT_MAX_PEERS];   // nullable entries
 };
 
 

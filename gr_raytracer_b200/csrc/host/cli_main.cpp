@@ -11,7 +11,8 @@
 //      | blackbody-spectrum [--min-temperature 1000 --max-temperature 10000 --min-redshift 0.5 --max-redshift 2
 //                            --width 1000 --height 1000 --filename blackbody_spectrum.png]
 //
-// Extra (not in the reference): --resource-root DIR (prefix for relative texture paths), --device N, and
+// Extra (not in the reference): --resource-root DIR (prefix for relative texture paths), --device N, --devices LIST
+// (e.g. 0-7: one frame sharded over several GPUs inside grrt_render, grrt_init_multi), and
 // render-frames: the reference's camera fly-through (scripts/Readme.md) runs the binary once per camera position;
 // here one process keeps the scene resident on the GPU, replaces only the camera per frame and encodes frame k on a
 // host thread while the GPU renders frame k+1.  positions.csv: one `x,y,z[,phi,theta,psi]` per line (other lines
@@ -55,6 +56,33 @@ bool ends_with(const std::string& s, const char* suf) {
     return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
 }
 
+// --devices: comma-separated ordinals and ranges, e.g. 0-7 or 0,2,5-6
+std::vector<int> parse_devices(const std::string& spec) {
+    std::vector<int> out;
+    size_t p = 0;
+    while (p <= spec.size()) {
+        size_t q = spec.find(',', p);
+        if (q == std::string::npos) q = spec.size();
+        const std::string tok = spec.substr(p, q - p);
+        const size_t dash = tok.find('-');
+        char* end = nullptr;
+        long a = std::strtol(tok.c_str(), &end, 10), b = a;
+        bool ok = !tok.empty() && end != tok.c_str();
+        if (ok && dash != std::string::npos) {
+            ok = end == tok.c_str() + dash;
+            const char* rest = tok.c_str() + dash + 1;
+            b = std::strtol(rest, &end, 10);
+            ok = ok && end != rest && *end == '\0' && b >= a;
+        } else if (ok) {
+            ok = *end == '\0';
+        }
+        if (!ok || a < 0 || b > 1023) die("invalid value '" + spec + "' for '--devices' (expected e.g. 0-7 or 0,2,4)");
+        for (long d = a; d <= b; ++d) out.push_back((int)d);
+        p = q + 1;
+    }
+    return out;
+}
+
 // --output-pattern holds exactly one conversion of the form %d or %0Nd (N = 1..9), which is replaced by the frame number;
 // "%%" is a literal per cent sign.  The pattern never reaches printf.
 std::string frame_file_name(const std::string& pattern, long long frame) {
@@ -91,6 +119,7 @@ int main(int argc, char** argv) {
     long long from_row = -1, from_col = -1, to_row = -1, to_col = -1, ray_row = -1, ray_col = -1;
     std::vector<double> at_pos, at_dir;
     int device = 0;
+    std::vector<int> devices;   // --devices 0-7 | 0,2,4: the frame is sharded over these GPUs inside grrt_render
 
     std::vector<std::string> args(argv + 1, argv + argc);
     auto value = [&](size_t& i, const std::string& flag) -> std::string {
@@ -140,6 +169,7 @@ int main(int argc, char** argv) {
         } else if (flag == "--config-file" || flag == "-c") config_file = value(i, flag);
         else if (flag == "--resource-root") resource_root = value(i, flag);
         else if (flag == "--device") device = std::atoi(value(i, flag).c_str());
+        else if (flag == "--devices") devices = parse_devices(value(i, flag));
         else if (flag == "--filename") filename = value(i, flag);
         else if (flag == "--from-row") from_row = std::atoll(value(i, flag).c_str());
         else if (flag == "--from-col") from_col = std::atoll(value(i, flag).c_str());
@@ -217,7 +247,12 @@ int main(int argc, char** argv) {
     if (rc) die(err);
     const GrrtScene* scene = grrt_host_scene_get(hs);
     GrrtCtx* ctx = nullptr;
-    if (grrt_init(device, &ctx) != 0) die("no usable CUDA device (sm_100): grrt has no CPU fallback");
+    if (!devices.empty()) {
+        if (grrt_init_multi((int)devices.size(), devices.data(), &ctx) != 0)
+            die("--devices: needs 1.." + std::to_string(GRRT_MAX_PEERS) + " distinct sm_100 CUDA devices with peer access to the first");
+    } else if (grrt_init(device, &ctx) != 0) {
+        die("no usable CUDA device (sm_100): grrt has no CPU fallback");
+    }
 
     if (action == "render-frames") {
         if (positions_file.empty()) die("render-frames needs --camera-positions");

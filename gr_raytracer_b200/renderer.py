@@ -103,7 +103,7 @@ class DeviceEngine:
 
     def wrap(self, ptr, shape, dtype):
         """A torch view of raw device memory (not owned by torch)."""
-        typestr = {torch.float64: "<f8", torch.uint8: "|u1"}[dtype]
+        typestr = {torch.float64: "<f8", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
 
         class _Raw:
             pass
@@ -111,9 +111,13 @@ class DeviceEngine:
         raw.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
         return torch.as_tensor(raw, device=self.device)
 
-    def trace_peers(self, items, n_items, rect, spa, xyza_ptrs, cls_ptrs, stop_ptrs):
+    def trace_peers(self, items, n_items, rect, spa, xyza_ptrs, cls_ptrs, stop_ptrs, steps_ptrs=None, item_offset=0,
+                    item_stride=1):
         self.ctx.trace_items_device_peers(self.dscene, self._p(items), n_items, rect, spa, xyza_ptrs, cls_ptrs, stop_ptrs,
-                                          self._p(self.counters), self._stream())
+                                          self._p(self.counters), self._stream(), steps_ptrs, item_offset, item_stride)
+
+    def order_by_cost(self, selected, n_selected, steps, ordered):
+        self.ctx.order_by_cost_device(self._p(selected), n_selected, self._p(steps), self._p(ordered), self._stream())
 
 
 class FrameRenderer:
@@ -134,8 +138,9 @@ class FrameRenderer:
             self.xyza = engine.new((n, 4), torch.float64)
             self.cls = engine.new((n,), torch.uint8)
             self.stop = engine.new((n,), torch.uint8)
-        self.steps = engine.new((n,), torch.int32)
+            self.steps = engine.new((n,), torch.int32)
         self.selected = engine.new((n,), torch.int32)
+        self.ordered = engine.new((n,), torch.int32)   # flagged pixels by descending base-pass step count
         self.count = engine.new((1,), torch.int32)
         if world > 1:
             ids = tile_interleaved_items(self.W, self.H, rank, world)
@@ -155,6 +160,7 @@ class FrameRenderer:
             self.loc_steps = engine.new((m,), torch.int32)
             self.gat_xyza = engine.new((world, m, 4), torch.float64)
             self.gat_meta = engine.new((world, m, 2), torch.uint8)
+            self.gat_steps = engine.new((world, m), torch.int32)
         self.last = {}
         self.profile = False   # True: CUDA-event timestamps of the phases of render() in self.phase_ms (adds syncs)
         self.phase_ms = {}
@@ -166,24 +172,24 @@ class FrameRenderer:
         import torch.distributed as dist
         e, n, world = self.e, self.n, self.world
         ok = 1
-        sizes = (n * 32, n, n)
+        sizes = (n * 32, n, n, n * 4)
         try:
             own = [e.shared_alloc(sz) for sz in sizes]
         except Exception:
             own, ok = [], 0
         self._own = [p for p, _ in own]
-        blob = b"".join(h for _, h in own) if ok else bytes(192)
+        blob = b"".join(h for _, h in own) if ok else bytes(256)
         mine = torch.tensor(list(blob), dtype=torch.uint8, device=e.device)
-        allh = torch.empty((world, 192), dtype=torch.uint8, device=e.device)
+        allh = torch.empty((world, 256), dtype=torch.uint8, device=e.device)
         dist.all_gather_into_tensor(allh.view(-1), mine, group=self.group)
         flag = torch.tensor([ok], dtype=torch.int32, device=e.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        peers = [[None] * world for _ in range(3)]
+        peers = [[None] * world for _ in range(4)]
         if int(flag.item()):
             allh = allh.cpu().numpy()
             try:
                 for r in range(world):
-                    for b in range(3):
+                    for b in range(4):
                         if r == self.rank:
                             peers[b][r] = self._own[b]
                         else:
@@ -199,10 +205,11 @@ class FrameRenderer:
         if not int(flag.item()):
             self.close()
             return
-        self.peer_xyza, self.peer_cls, self.peer_stop = peers
+        self.peer_xyza, self.peer_cls, self.peer_stop, self.peer_steps = peers
         self.xyza = e.wrap(self._own[0], (n, 4), torch.float64)
         self.cls = e.wrap(self._own[1], (n,), torch.uint8)
         self.stop = e.wrap(self._own[2], (n,), torch.uint8)
+        self.steps = e.wrap(self._own[3], (n,), torch.int32)
         self._flag = torch.zeros(1, dtype=torch.int32, device=e.device)
         self.p2p = True
 
@@ -228,8 +235,21 @@ class FrameRenderer:
         import torch.distributed as dist
         dist.all_gather_into_tensor(out, inp, group=self.group)
 
+    def _order(self, n_sel):
+        """Flagged pixels by descending base-pass step count (the base pass is the pilot of the second pass; stable, so
+        every rank derives the same list).  Traced in this order the work queue ends on short rays, and dealing the list
+        round-robin gives every rank the same share of the expensive pixels.  The image does not depend on the order."""
+        e = self.e
+        if hasattr(e, "order_by_cost"):
+            e.order_by_cost(self.selected, n_sel, self.steps, self.ordered)
+        else:   # engines without the device sort (the CPU stand-in of the tests): same stable order with torch
+            sel = self.selected[:n_sel].long()
+            idx = torch.sort(-self.steps[sel].long(), stable=True).indices
+            self.ordered[:n_sel] = self.selected[:n_sel][idx]
+
     def render(self):
-        """Renders the frame into self.xyza / cls / stop / steps (device).  Returns ray counts."""
+        """Renders the frame into self.xyza / cls / stop / steps (device; steps = accepted steps of the 1-spp ray).
+        Returns ray counts."""
         e, ad = self.e, self.ad
         marks = []
 
@@ -243,7 +263,9 @@ class FrameRenderer:
         if self.world == 1:
             e.trace(None, self.n, self.rect, 0, self.xyza, self.cls, self.stop, self.steps)
         elif self.p2p:
-            e.trace_peers(self.my_items, self.n_mine, self.rect, 0, self.peer_xyza, self.peer_cls, self.peer_stop)
+            # no rank may store pixels of this frame into a peer that is still reading (or copying out) the previous one
+            self._barrier()
+            e.trace_peers(self.my_items, self.n_mine, self.rect, 0, self.peer_xyza, self.peer_cls, self.peer_stop, self.peer_steps)
             mark("base")
             self._barrier()
         else:
@@ -252,16 +274,20 @@ class FrameRenderer:
             meta = torch.stack((self.loc_cls, self.loc_stop), dim=1)
             self._all_gather(self.gat_xyza.view(-1, 4), self.loc_xyza)
             self._all_gather(self.gat_meta.view(-1, 2), meta)
+            self._all_gather(self.gat_steps.view(-1), self.loc_steps)
             self.xyza.index_copy_(0, self.gather_dst, self.gat_xyza.view(-1, 4).index_select(0, self.gather_src))
             meta_all = self.gat_meta.view(-1, 2).index_select(0, self.gather_src)
             self.cls.index_copy_(0, self.gather_dst, meta_all[:, 0].contiguous())
             self.stop.index_copy_(0, self.gather_dst, meta_all[:, 1].contiguous())
+            self.steps.index_copy_(0, self.gather_dst, self.gat_steps.view(-1).index_select(0, self.gather_src))
         mark("gather_base")
         n_sel = 0
         min_lum = 0.0
         if ad.enabled or ad.show_sampling_mask:
             min_lum = e.select(self.xyza, self.cls, self.H, self.W, self.selected, self.count)
             n_sel = int(self.count.item())
+            if n_sel and not ad.show_sampling_mask:
+                self._order(n_sel)
             mark("mask")
             if self.p2p:
                 self._barrier()   # no rank may store sub-sample means into a frame whose mask is still being computed
@@ -271,16 +297,17 @@ class FrameRenderer:
             elif n_sel:
                 spa = int(ad.samples_per_axis)
                 if self.world == 1:
-                    e.trace(self.selected, n_sel, self.rect, spa, self.xyza)
+                    e.trace(self.ordered, n_sel, self.rect, spa, self.xyza)
                 elif self.p2p:
-                    mine = self.selected[:n_sel][self.rank::self.world].contiguous()
-                    if int(mine.numel()):
-                        e.trace_peers(mine, int(mine.numel()), self.rect, spa, self.peer_xyza, self.peer_cls, self.peer_stop)
+                    k = (n_sel - self.rank + self.world - 1) // self.world if self.rank < n_sel else 0
+                    if k:   # every world-th pixel of the cost-ordered list, starting at this rank
+                        e.trace_peers(self.ordered, k, self.rect, spa, self.peer_xyza, self.peer_cls, self.peer_stop,
+                                      None, self.rank, self.world)
                     mark("supersample")
                     self._barrier()
                 else:
-                    # flagged pixels dealt round-robin; every rank writes its means into a frame-sized scratch
-                    mine = self.selected[:n_sel][self.rank::self.world].contiguous()
+                    # flagged pixels dealt round-robin in cost order; every rank writes its means into a frame-sized scratch
+                    mine = self.ordered[:n_sel][self.rank::self.world].contiguous()
                     k = int(mine.numel())
                     per = (n_sel + self.world - 1) // self.world
                     loc = self.e.new((per, 4), torch.float64)
@@ -292,7 +319,7 @@ class FrameRenderer:
                     gat = self.e.new((self.world, per, 4), torch.float64)
                     self._all_gather(gat.view(-1, 4), loc)
                     for r in range(self.world):
-                        ids = self.selected[:n_sel][r::self.world].long()
+                        ids = self.ordered[:n_sel][r::self.world].long()
                         self.xyza.index_copy_(0, ids, gat[r, :ids.numel()])
         mark("end")
         if self.profile:

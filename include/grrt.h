@@ -34,6 +34,8 @@
 extern "C" {
 #endif
 
+#define GRRT_MAX_PEERS 8   /* devices of one multi-device context / frames one kernel launch can store into */
+
 /* ---- enums (values are ABI) ------------------------------------------------------ */
 
 /* configuration.rs:110-129 GeometryType */
@@ -237,6 +239,16 @@ typedef struct GrrtDeviceScene GrrtDeviceScene;
 /* Create a context bound to one CUDA device.  Fails with GRRT_ERR_CUDA when there is
  * no usable sm_100 device: there is no CPU fallback. */
 int grrt_init(int device_id, GrrtCtx** out);
+/* One context over n_devices (1..GRRT_MAX_PEERS, distinct) GPUs of one node driven by this process -- the
+ * grrt_init(n_devices, device_ids) of SURVEY.md 8(b).  The reference's entry point is one blocking call of one process
+ * (src/main.rs:106-115 -> raytracer.rs:460-497); grrt_render / grrt_render_resident on such a context are likewise
+ * blocking and shard the frame internally: 8x4-pixel tiles are dealt round-robin to the devices, every device stores
+ * its finished pixels straight into the frame held by device_ids[0] (peer stores over NVLink from inside the trace
+ * kernel; there is no reduction, so no collective and no gather pass), the flagged pixels are dealt in descending
+ * base-pass cost.  The frame is bit for bit the single-device frame.  Needs peer access from every device to
+ * device_ids[0] (GRRT_ERR_CUDA otherwise).  Scenes must be uploaded through the same context. */
+int grrt_init_multi(int n_devices, const int* device_ids, GrrtCtx** out);
+int grrt_device_count(const GrrtCtx* ctx);   /* 1 for grrt_init contexts */
 void grrt_destroy(GrrtCtx* ctx);
 const char* grrt_last_error(const GrrtCtx* ctx);
 const char* grrt_version(void);
@@ -309,17 +321,27 @@ int grrt_trace_items_device(GrrtCtx* ctx, const GrrtDeviceScene* dscene,
  * all `n_peers` frames (own pointer included) straight from the trace kernel / the sub-sample
  * mean kernel.  The pointer arrays are HOST arrays of device pointers.  The caller orders the
  * passes across ranks (a barrier after each call) before reading its frame. */
-#define GRRT_MAX_PEERS 8
 int grrt_ipc_alloc(GrrtCtx* ctx, size_t bytes, void** d_ptr, unsigned char handle_out[64]);
 int grrt_ipc_open(GrrtCtx* ctx, const unsigned char handle[64], void** d_ptr);
 int grrt_ipc_close(GrrtCtx* ctx, void* d_ptr);
 int grrt_ipc_free(GrrtCtx* ctx, void* d_ptr);
+/* Item i of the call is d_items[item_offset + i * item_stride] (item_stride >= 1): a rank's share of a list
+ * that is dealt round-robin.  d_steps_peers (and each of its entries) may be NULL. */
 int grrt_trace_items_device_peers(GrrtCtx* ctx, const GrrtDeviceScene* dscene,
-                                  const uint32_t* d_items, uint64_t n_items,
+                                  const uint32_t* d_items, uint64_t item_offset, uint64_t item_stride,
+                                  uint64_t n_items,
                                   uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
                                   uint32_t samples_per_axis, uint32_t n_peers,
                                   double* const* d_xyza_peers, uint8_t* const* d_class_peers,
-                                  uint8_t* const* d_stop_peers, uint64_t* d_counters, void* cuda_stream);
+                                  uint8_t* const* d_stop_peers, uint32_t* const* d_steps_peers,
+                                  uint64_t* d_counters, void* cuda_stream);
+
+/* The base pass as pilot of the supersampling pass (BASELINE.json north_star: "load-balanced from a pilot ...
+ * pass"): orders the flagged pixel ids by descending base-pass step count (stable, ties keep pixel order).
+ * Tracing the list in that order ends the work queue on short rays; dealing it round-robin gives every
+ * device the same share of the expensive pixels.  The image does not depend on the order. */
+int grrt_order_by_cost_device(GrrtCtx* ctx, const uint32_t* d_selected, uint32_t n_selected,
+                              const uint32_t* d_steps /* per pixel id */, uint32_t* d_ordered, void* cuda_stream);
 
 /* resolve_minimum_luminance + collect_pixels_to_supersample (raytracer.rs:118-129,
  * 386-458) over a complete base buffer of rows x cols pixels on the device.  Writes the
