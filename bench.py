@@ -135,6 +135,8 @@ def run_reference(args, wl):
     from gr_raytracer_b200 import abi
     from oracle import scene as osc
     ensure_resources()
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every host core regardless
+    osc.lib().orc_set_num_threads(len(os.sched_getaffinity(0)) or 1)
     opts = abi.default_cli_opts(**wl["opts"])
     oscene = osc.scene_from_toml(os.path.join(ROOT, wl["toml"]), opts, ROOT)
     W, H = wl["opts"]["width"], wl["opts"]["height"]
@@ -155,7 +157,11 @@ def run_reference(args, wl):
         "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "rkf45_steps_per_s": tot["steps"] / t_all, "rkf45_attempts_per_s": tot["attempts"] / t_all,
-        "config": {"workload": args.workload + ": " + wl["desc"], "sampled": True},
+        "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H, "sampled": True,
+                   "sample": res["sample"], "cores": res["cores"],
+                   "note": "same scene, camera and command line as the GPU arm; each step traces a bounded sample of the frame "
+                           "(evenly spread 4-row strips, base pass + mask + supersampling inside each strip) and the rate is "
+                           "per ray, so it compares with the GPU arm's whole-frame rate"},
         "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": res["cores"], "kind": "port", "sample": res["sample"],
                          "note": "C++ oracle (restatement of the Rust reference, OpenMP over pixels); the reference needs cargo, absent here"},
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,6 +191,169 @@ def scene_h2d_bytes(sc):
     return total + C.sizeof(abi.GrrtScene)
 
 
+# expected seconds of one full frame (base + adaptive pass) on ONE B200, measured in round 2 (profiles/r2_fullsize_*.json):
+# sizes the per-scene block so that the default run stays within minutes
+EXPECTED_S_1GPU = {"C1": 0.3, "C2": 0.25, "C3": 175.0, "C4": 350.0, "C5": 125.0}
+PER_SCENE_ORDER = ["C1", "C3", "C4", "C5"]
+
+
+class Bench:
+    """One process per GPU (torchrun for N > 1); frames are rendered device-resident by FrameRenderer."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from gr_raytracer_b200 import api
+        self.torch, self.dist, self.api = torch, dist, api
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        if args.gpus > 1 and self.world == 1:
+            raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: libgrrt has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.cpu_group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.cpu_group = dist.new_group(backend="gloo")   # host-side waits that leave the GPUs idle
+        if self.rank == 0:
+            ensure_resources()
+        if self.world > 1:
+            dist.barrier()
+        self.ctx = api.Context(self.local_rank)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        self.dfma_rate, _ = self.ctx.measure_fp64_peak()   # FP64 roofline denominator, measured here
+        self.peak_tflops = 2.0 * self.dfma_rate / 1e12
+
+    def sync_all(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        """Waits on the CPU (gloo): unlike an NCCL barrier no kernel spins on the waiting ranks' GPUs."""
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
+
+    def reduce(self, values, op):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return [float(v) for v in t.tolist()]
+
+    def time_frames(self, wl, steps, warmup, rect=None, want_clocks=False):
+        """Renders warmup + steps frames of a workload (all ranks), device-timed per frame, max over ranks."""
+        torch = self.torch
+        from gr_raytracer_b200 import abi
+        from gr_raytracer_b200.renderer import DeviceEngine, FrameRenderer
+        opts = abi.default_cli_opts(**wl["opts"])
+        scene = self.api.HostScene(os.path.join(ROOT, wl["toml"]), opts, ROOT)
+        sc = scene.c
+        W, H = int(sc.camera.cols), int(sc.camera.rows)
+        engine = DeviceEngine(self.ctx, scene)
+        fr = FrameRenderer(engine, sc.adaptive, W, H, self.rank, self.world, rect=rect)
+        for _ in range(warmup):
+            fr.render()
+            self.flush.fill_(1)
+        self.sync_all()
+        engine.counters.zero_()
+        launches0 = self.ctx.launch_count()
+        sampler = None
+        if want_clocks:
+            sampler = ClockSampler(self.local_rank)
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        counts = None
+        self.sync_all()
+        for i in range(steps):
+            ev[i][0].record()
+            counts = fr.render()
+            ev[i][1].record()
+            self.flush.fill_(i & 1)       # L2 flush between timed iterations (not timed)
+        self.sync_all()
+        clocks = sampler.finish() if sampler else None
+        launches = self.ctx.launch_count() - launches0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        ms = self.reduce([ms], "MAX")[0]
+        cnt = engine.counters.clone()
+        if self.world > 1:
+            self.dist.all_reduce(cnt, op=self.dist.ReduceOp.SUM)
+        launches = int(self.reduce([launches], "SUM")[0])
+        cnt = [int(v) for v in cnt.tolist()]
+        secs = ms * 1e-3
+        rays = (counts["rays_base"] + counts["rays_supersample"]) * steps
+        flops = algorithmic_flops(sc.geometry.kind, cnt[0], cnt[1], cnt[2])
+        res = dict(scene=scene, engine=engine, fr=fr, W=W, H=H, ms_per_frame=ms / steps, secs=secs, rays_per_frame=rays // steps,
+                   pixels_supersampled=counts["pixels_supersampled"], mrays=rays / secs / 1e6, steps_per_s=cnt[1] / secs,
+                   attempts_per_s=cnt[0] / secs, samples_per_s=cnt[2] / secs, ray_errors=cnt[3],
+                   stop_histogram=[c // steps for c in cnt[8:14]], flops=flops, tflops=flops / secs / 1e12,
+                   launches=launches, clocks=clocks, p2p=fr.p2p)
+        return res
+
+    def close_frames(self, res):
+        res["fr"].close()
+        res["engine"].close()
+        res["scene"].close()
+
+
+def per_scene_block(bench, budget_s):
+    """One frame of every other BASELINE.json configuration (the headline workload is timed separately), full size
+    while the time budget lasts; a configuration that does not fit is rendered on a centred band of rows sized from
+    the round-2 full-frame measurements (its rates are per ray / per step, hence comparable)."""
+    out = {}
+    world = bench.world
+    t_start = time.perf_counter()
+    for name in PER_SCENE_ORDER:
+        wl = WORKLOADS[name]
+        W, H = wl["opts"]["width"], wl["opts"]["height"]
+        left = budget_s - (time.perf_counter() - t_start)
+        left = bench.reduce([left], "MIN")[0]                 # every rank takes the same decision
+        expect = EXPECTED_S_1GPU[name] / world * 1.2 + 3.0      # + scene set-up, texture upload
+        rect, full = None, True
+        if expect > left:
+            frac = (left - 3.0) / (EXPECTED_S_1GPU[name] / world * 1.5)   # the centre rows are the expensive ones
+            rows = int(H * frac) // 4 * 4
+            if rows < 16:
+                out[name] = {"workload": wl["desc"], "skipped": f"time budget of the per-scene block used up ({budget_s:.0f} s); "
+                             f"a full frame takes about {EXPECTED_S_1GPU[name] / world:.0f} s on {world} GPU(s): profiles/r2_fullsize_{name}.json"}
+                continue
+            r0 = (H - rows) // 2
+            rect, full = (r0, 0, r0 + rows, W), False
+        frames = 3 if EXPECTED_S_1GPU[name] < 2.0 else 1
+        r = bench.time_frames(wl, frames, 1 if frames > 1 else 0, rect=rect)
+        entry = {"workload": wl["desc"], "full_frame": full, "frames_timed": frames, "ms_per_frame": r["ms_per_frame"],
+                 "mrays_per_s": r["mrays"], "rays_per_frame": r["rays_per_frame"], "pixels_supersampled": r["pixels_supersampled"],
+                 "rkf45_steps_per_s": r["steps_per_s"], "rkf45_attempts_per_s": r["attempts_per_s"],
+                 "raymarch_samples_per_s": r["samples_per_s"], "stop_histogram": r["stop_histogram"], "ray_errors": r["ray_errors"],
+                 "algorithmic_tflops": r["tflops"], "roofline_frac": r["tflops"] / (bench.peak_tflops * world),
+                 "build": "exact (no FMA: the issue-slot ceiling is half the DFMA peak)" if name in ("C3", "C4") else "FMA",
+                 "parity": PARITY_RECORD.get(name)}
+        if rect:
+            entry["section"] = {"from_row": rect[0], "to_row": rect[2], "from_col": rect[1], "to_col": rect[3],
+                                "note": "centred band of rows of the full-size frame (the reference CLI's --from-row/--to-row); "
+                                        "the whole frame is recorded in profiles/r2_fullsize_%s.json" % name}
+        out[name] = entry
+        bench.close_frames(r)
+    return out
+
+
+# where each configuration's parity at its stated size is established (tests/ run by `pytest -m gpu`; the oracle is
+# not used by this file outside the cpu_baseline leg)
+PARITY_RECORD = {
+    "C1": "tests/test_gpu_fullsize.py::test_full_frame_parity_gate[C1]: 250000 of 250000 pixels of the 500x500 frame inside the gate",
+    "C2": "tests/test_gpu_fullsize.py::test_full_frame_parity_gate[C2]: 99.999 % of the 1500x1500 frame inside the gate (21 outliers listed)",
+    "C3": "tests/test_gpu_fullsize.py::test_kerr_schild_configs_at_stated_size[C3] + profiles/r2_fullsize_C3.json: 300 of 300 sampled pixels "
+          "(30 shadow rays > 1e5 steps) bit-equal step counts, XYZ within 1e-12",
+    "C4": "tests/test_gpu_fullsize.py::test_kerr_schild_configs_at_stated_size[C4] + profiles/r2_fullsize_C4.json: 300 of 300 sampled pixels",
+    "C5": "profiles/r2_fullsize_C5_*.json (sampled pixels at 4096x4096 / 8192x8192) + tests/test_reference_image.py (Perlin pinned against the reference's own render)",
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,6 +364,8 @@ def main():
     ap.add_argument("--width", type=int, default=None, help="override the workload's frame size (not a bench value)")
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-scene-budget-s", type=float, default=420.0,
+                    help="seconds the per-scene block (one frame each of C1, C3, C4, C5) may take; 0 disables it")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     wl["opts"] = dict(wl["opts"])
@@ -206,78 +377,16 @@ def main():
         return run_reference(args, wl)
 
     import torch
-    import torch.distributed as dist
-    from gr_raytracer_b200 import abi, api
-    from gr_raytracer_b200.renderer import DeviceEngine, FrameRenderer
+    from gr_raytracer_b200 import abi
+    bench = Bench(args)
+    rank, world, ctx, dist = bench.rank, bench.world, bench.ctx, bench.dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if args.gpus > 1 and world == 1:
-        raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: libgrrt has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ensure_resources() if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-
-    opts = abi.default_cli_opts(**wl["opts"])
-    scene = api.HostScene(os.path.join(ROOT, wl["toml"]), opts, ROOT)
+    # ---- headline workload: K timed frames ----
+    r = bench.time_frames(wl, args.steps, args.warmup, want_clocks=True)
+    scene, engine, fr = r["scene"], r["engine"], r["fr"]
     sc = scene.c
-    W, H = int(sc.camera.cols), int(sc.camera.rows)
-    ctx = api.Context(local_rank)
-    engine = DeviceEngine(ctx, scene)
-    fr = FrameRenderer(engine, sc.adaptive, W, H, rank, world)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # FP64 roofline denominator, measured here (MEASURED_PEAKS.json carries no FP64 number)
-    dfma_rate, _ = ctx.measure_fp64_peak()
-
-    for _ in range(args.warmup):
-        fr.render()
-        flush.fill_(1)
-    sync_all()
-    engine.counters.zero_()
-    launches0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    counts = None
-    sync_all()
-    for i in range(args.steps):
-        ev[i][0].record()
-        counts = fr.render()
-        ev[i][1].record()
-        flush.fill_(i & 1)       # L2 flush between timed iterations (not timed)
-    sync_all()
-    clocks = sampler.finish()
-    launches = ctx.launch_count() - launches0
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    cnt = engine.counters.clone()
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
-    ms = float(t.item())
-    cnt = [int(v) for v in cnt.tolist()]
-    attempts, accepted, samples, errors = cnt[0], cnt[1], cnt[2], cnt[3]
-    rays_per_step = counts["rays_base"] + counts["rays_supersample"]
-    secs = ms * 1e-3
-    mrays = rays_per_step * args.steps / secs / 1e6
-    flops = algorithmic_flops(sc.geometry.kind, attempts, accepted, samples)
+    W, H = r["W"], r["H"]
+    launches = r["launches"]
 
     # per-kernel time of the dominant kernel (trace_kernel): separate timed pass with events around each launch
     kern_ms, kern_flops = None, None
@@ -289,15 +398,15 @@ def main():
         engine.trace(None, fr.n, fr.rect, 0, fr.xyza, fr.cls, fr.stop, fr.steps)
         e1.record()
         torch.cuda.synchronize()
-        base_cnt = [int(v) for v in engine.counters.tolist()]
         n_sel = 0
         if sc.adaptive.enabled and not sc.adaptive.show_sampling_mask:
             engine.select(fr.xyza, fr.cls, H, W, fr.selected, fr.count)
             n_sel = int(fr.count.item())
         ss_ms = 0.0
         if n_sel:
+            engine.order_by_cost(fr.selected, n_sel, fr.steps, fr.ordered)
             e2.record()
-            engine.trace(fr.selected, n_sel, fr.rect, int(sc.adaptive.samples_per_axis), fr.xyza)
+            engine.trace(fr.ordered, n_sel, fr.rect, int(sc.adaptive.samples_per_axis), fr.xyza)
             e3.record()
             torch.cuda.synchronize()
             ss_ms = e2.elapsed_time(e3)   # includes the (tiny) resolve kernel
@@ -306,97 +415,118 @@ def main():
         kern_ms = (e0.elapsed_time(e1) + ss_ms) / n_launch
         kern_flops = algorithmic_flops(sc.geometry.kind, tot_cnt[0], tot_cnt[1], tot_cnt[2]) / n_launch
 
-    # end to end through the C ABI with host buffers (grrt_render: upload scene, trace, read back)
+    # ---- N > 1: the N-rank frame must equal the frame one GPU renders alone ----
+    bit_identical = None
+    if world > 1:
+        fr.render()
+        bench.sync_all()
+        if rank == 0:
+            alone = ctx.render(scene)
+            got = fr.xyza.cpu().numpy().reshape(H, W, 4)
+            bit_identical = bool(np.array_equal(got, alone["xyza"]) and
+                                 np.array_equal(fr.cls.cpu().numpy().reshape(H, W), alone["ray_class"]) and
+                                 np.array_equal(fr.stop.cpu().numpy().reshape(H, W), alone["stop"]) and
+                                 np.array_equal(fr.steps.cpu().numpy().reshape(H, W).view(np.uint32), alone["steps"]))
+        bench.sync_all()
+
+    # ---- end to end through the C ABI with HOST buffers: grrt_render uploads the scene, traces, reads the frame back ----
+    # N > 1: rank 0 drives all N GPUs through ONE multi-device context (grrt_init_multi), the drop-in call a host program
+    # makes; the other ranks wait at the barrier with their GPUs idle.
     e2e = None
-    if world == 1:
-        npx = W * H   # results land in pinned host memory
+    npx = W * H
+    bench.sync_all()
+    bench.host_barrier()
+    if rank == 0:
         pinned = {"xyza": torch.empty((npx, 4), dtype=torch.float64).pin_memory().numpy(),
                   "ray_class": torch.empty(npx, dtype=torch.uint8).pin_memory().numpy(),
                   "stop": torch.empty(npx, dtype=torch.uint8).pin_memory().numpy(),
                   "steps": torch.empty(npx, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+        group = ctx if world == 1 else bench.api.Context(list(range(world)))
         for _ in range(2):
-            ctx.render(scene, out=pinned)  # warm
-        t0 = time.perf_counter()
+            out = group.render(scene, out=pinned)  # warm
         reps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
         for _ in range(reps):
-            out = ctx.render(scene, out=pinned)
+            out = group.render(scene, out=pinned)
         dt = (time.perf_counter() - t0) / reps
         st = out["stats"]
         e2e_rays = st["rays_base"] + st["rays_supersample"]
-        d2h = W * H * (32 + 1 + 1 + 4) + 16 * 8
-        e2e = {"value": e2e_rays / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": scene_h2d_bytes(sc), "d2h_bytes_per_step": d2h,
-               "ms_per_step": dt * 1e3, "api": "grrt_render (C ABI, host buffers)"}
-    else:
-        # N > 1: the public multi-GPU call is FrameRenderer.render(); every step uploads the scene again on every
-        # rank (host -> device) and rank 0 reads the finished frame back into pinned host memory
-        host = torch.empty((W * H, 4), dtype=torch.float64).pin_memory() if rank == 0 else None
-        reps = max(1, min(args.steps, 5))
-        c2 = None
-        for rep in range(reps + 1):
-            if rep == 1:   # rep 0 warms up
-                sync_all()
-                t0 = time.perf_counter()
-            engine.reupload()
-            c2 = fr.render()
-            if rank == 0:
-                host.copy_(fr.xyza, non_blocking=True)
-            torch.cuda.synchronize()
-        sync_all()
-        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": (c2["rays_base"] + c2["rays_supersample"]) / float(dt.item()) / 1e6, "unit": "Mrays/s",
-               "h2d_bytes_per_step": scene_h2d_bytes(sc) * world, "d2h_bytes_per_step": W * H * 32,
-               "ms_per_step": float(dt.item()) * 1e3,
-               "api": "DeviceEngine.reupload + FrameRenderer.render on every rank, frame read back on rank 0 (pinned)"}
-        del host
+        d2h = W * H * (32 + 1 + 1 + 4) + 16 * 8 * world
+        e2e = {"value": e2e_rays / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": scene_h2d_bytes(sc) * world,
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
+               "api": "grrt_render (C ABI, host buffers)" if world == 1 else
+                      f"grrt_render on one grrt_init_multi context over {world} GPUs (C ABI, host buffers, one process)"}
+        if world > 1:
+            e2e["bit_identical_to_1gpu"] = bool(np.array_equal(out["xyza"], alone["xyza"]) and np.array_equal(out["steps"], alone["steps"]))
+            group.close()
+    bench.host_barrier()
+    headline = {k: r[k] for k in ("ms_per_frame", "mrays", "steps_per_s", "attempts_per_s", "samples_per_s", "ray_errors", "tflops",
+                                  "rays_per_frame", "pixels_supersampled", "clocks", "p2p", "stop_histogram", "secs", "flops")}
+    bench.close_frames(r)
+
+    # ---- the other configurations ----
+    per_scene = per_scene_block(bench, args.per_scene_budget_s) if (args.per_scene_budget_s > 0 and args.workload == "C2"
+                                                                    and not args.width and not args.height) else None
 
     line = None
     if rank == 0:
-        peak_tflops = 2.0 * dfma_rate / 1e12
+        peak_tflops = bench.peak_tflops
         roofline = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tflops,
                     "peak_source": "DFMA-chain microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); FMA = 2 flops",
                     "traffic": None}
         if args.workload == "C2" and (W, H) == (1500, 1500) and world == 1:
-            # dram__bytes_read.sum + dram__bytes_write.sum of the base-pass launch, ncu --set full capture of this command
-            roofline["traffic"] = 26.936320e6 + 75.075840e6
-            roofline["traffic_source"] = "profiles/r1_c2_trace_kernel_v12_1500.json (bytes per base-pass launch: the 85.5 MB of frame buffers written once, scene tables read once)"
+            roofline.update(C2_NCU_RECORD)
         if kern_ms:
             ach = kern_flops / (kern_ms * 1e-3) / 1e12
             roofline.update({"achieved": ach, "frac": ach / peak_tflops, "kernel": "trace_kernel", "kernel_ms_per_launch": kern_ms,
                              "algorithmic_flops_per_launch": kern_flops,
-                             "note": "algorithmic FP64 ops of SURVEY.md 8(d) (divisions, sqrt and libm calls count 1 each) over the "
-                                     "mean trace_kernel launch time; Kerr-Schild scenes run the contraction-free build (bit parity), "
-                                     "whose issue-slot ceiling is half the FMA peak; the other geometries run the FMA build"})
+                             "note": "algorithmic FP64 ops of SURVEY.md 8(d) (divisions, sqrt and libm calls count 1 each; the reference's "
+                                     "work on components nobody reads counts too) over the mean trace_kernel launch time; Kerr-Schild scenes "
+                                     "run the contraction-free build (bit parity), whose issue-slot ceiling is half the FMA peak; the other "
+                                     "geometries run the FMA build"})
         else:
-            ach = flops / secs / 1e12
+            ach = headline["tflops"]
             roofline.update({"achieved": ach, "frac": ach / (peak_tflops * world), "kernel": "whole step, all ranks"})
         line = {
-            "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "metric": "Mrays/s", "value": headline["mrays"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": headline["ms_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H, "l2": "256 MiB flush write between timed steps",
-                       "partition": "whole frame" if world == 1 else f"8x4 tiles round-robin over {world} ranks",
+                       "partition": "whole frame" if world == 1 else f"8x4 tiles round-robin over {world} ranks; flagged pixels dealt "
+                                    "round-robin in descending base-pass step count",
                        "exchange": "none" if world == 1 else ("peer stores from the trace kernel (cudaIpc over NVLink)"
-                                                              if fr.p2p else "NCCL all-gather"),
+                                                              if headline["p2p"] else "NCCL all-gather"),
                        "textures": "synthetic 2048x2048 atlases (scenes/make_textures.py)"},
-            "rays_per_step": rays_per_step, "pixels_supersampled": counts["pixels_supersampled"],
-            "rkf45_steps_per_s": accepted / secs, "rkf45_attempts_per_s": attempts / secs, "raymarch_samples_per_s": samples / secs,
-            "ray_errors": errors, "algorithmic_tflops": flops / secs / 1e12,
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
+            "rays_per_step": headline["rays_per_frame"], "pixels_supersampled": headline["pixels_supersampled"],
+            "rkf45_steps_per_s": headline["steps_per_s"], "rkf45_attempts_per_s": headline["attempts_per_s"],
+            "raymarch_samples_per_s": headline["samples_per_s"], "stop_histogram": headline["stop_histogram"],
+            "ray_errors": headline["ray_errors"], "algorithmic_tflops": headline["tflops"],
+            "gpu_launches": launches, "clocks": headline["clocks"], "roofline": roofline, "e2e": e2e,
         }
+        if bit_identical is not None:
+            line["bit_identical_to_1gpu"] = bit_identical
+        if per_scene is not None:
+            line["per_scene"] = per_scene
     # CPU baseline on rank 0 at N=1 only (bounded sample, all host cores)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import scene as osc
+        opts = abi.default_cli_opts(**wl["opts"])
         oscene = osc.scene_from_toml(os.path.join(ROOT, wl["toml"]), opts, ROOT)
         res = cpu_sample(osc, oscene, W, H, 20.0)
         line["cpu_baseline"] = {"value": res["rays"] / res["seconds"] / 1e6, "unit": "Mrays/s", "cores": res["cores"], "kind": "port",
                                 "sample": res["sample"], "rkf45_steps_per_s": res["steps"] / res["seconds"], "seconds": res["seconds"]}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    fr.close()
-    engine.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of the base-pass launch and the FP64-pipe figure from the ncu --set full capture
+# of this command (C2 1500x1500, one GPU); see profiles/
+C2_NCU_RECORD = {
+    "traffic": 26.936320e6 + 75.075840e6,
+    "traffic_source": "profiles/r1_c2_trace_kernel_v12_1500.json (bytes per base-pass launch: the 85.5 MB of frame buffers written once, scene tables read once)",
+}
 
 
 import ctypes as C  # noqa: E402

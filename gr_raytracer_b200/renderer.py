@@ -123,13 +123,15 @@ class DeviceEngine:
 class FrameRenderer:
     """One frame = base pass + mask + supersampling, sharded over `world` ranks."""
 
-    def __init__(self, engine, adaptive, width, height, rank=0, world=1, group=None):
+    def __init__(self, engine, adaptive, width, height, rank=0, world=1, group=None, rect=None):
+        """`rect` = (from_row, from_col, to_row, to_col): render that section of the width x height frame (the
+        reference's --from-row ... --to-col, cli.rs:63-74); pixel ids and the mask are then section-relative."""
         self.e, self.ad = engine, adaptive
-        self.W, self.H = int(width), int(height)
+        self.rect = (0, 0, int(height), int(width)) if rect is None else tuple(int(v) for v in rect)
+        self.W, self.H = self.rect[3] - self.rect[1], self.rect[2] - self.rect[0]
         self.rank, self.world, self.group = rank, world, group
         n = self.W * self.H
         self.n = n
-        self.rect = (0, 0, self.H, self.W)
         self.p2p = False
         self._own, self._opened = [], []
         if 1 < world <= abi.MAX_PEERS and getattr(engine, "supports_peers", False) and os.environ.get("GRRT_P2P", "1") != "0":

@@ -83,10 +83,18 @@ def test_full_frame_parity_gate(ctx, name):
     frac = float(good.mean())
     bad_r, bad_c = np.nonzero(~good)
     b = _impact_parameters(sc, bad_r[:40], bad_c[:40])
-    b_crit = 1.5 * np.sqrt(3.0) * sc.c.geometry.radius
+    rs = sc.c.geometry.radius
+    if sc.c.geometry.kind == abi.GEOM_KERR_BL:   # equatorial photon orbits of Kerr: b = +-(r_ph + 3 M)... quoted as the range of |b_crit|
+        m, a = 0.5 * rs, sc.c.geometry.a
+        r_pro = 2 * m * (1 + np.cos(2.0 / 3.0 * np.arccos(-a / m)))
+        r_ret = 2 * m * (1 + np.cos(2.0 / 3.0 * np.arccos(a / m)))
+        b_of = lambda r, sgn: abs(-(r ** 3 - 3 * m * r * r + a * a * r + a * a * m) / (a * (r - m))) if a else 3 * np.sqrt(3) * m
+        crit = f"Kerr a/M = {a / m:.3f}: photon-orbit impact parameters between {b_of(r_pro, 1):.3f} (prograde) and {b_of(r_ret, -1):.3f} (retrograde)"
+    else:
+        crit = f"Schwarzschild b_crit = {1.5 * np.sqrt(3.0) * rs:.4f}"
     print(f"[fullsize] {name} {W}x{H} full frame: {good.sum()} of {good.size} pixels ({frac * 100:.4f} %) within 1e-4 with identical "
           f"fate; worst in-gate rel err {rel[good].max():.2e}; steps equal on {(dev['steps'] == ora['steps']).mean() * 100:.4f} %; "
-          f"{len(bad_r)} outliers" + (f" (Schwarzschild b_crit = {b_crit:.4f})" if len(bad_r) else ""))
+          f"{len(bad_r)} outliers" + (f" ({crit})" if len(bad_r) else ""))
     for k in range(min(len(bad_r), 40)):
         r, c = bad_r[k], bad_c[k]
         print(f"    outlier ({r},{c}): rel err {rel[r, c]:.2e}, stop dev/oracle {dev['stop'][r, c]}/{ora['stop'][r, c]}, steps "
