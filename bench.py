@@ -315,7 +315,16 @@ def per_scene_block(bench, budget_s):
         left = bench.reduce([left], "MIN")[0]                 # every rank takes the same decision
         expect = EXPECTED_S_1GPU[name] / world * 1.2 + 3.0      # + scene set-up, texture upload
         rect, full = None, True
-        if expect > left:
+        if expect > left and name in ("C3", "C4"):
+            # Kerr-Schild frames are dominated by the shadow's crawling rays (up to 1e6 steps, ~20 s each), which sit in the
+            # middle of the frame: the only representative section is a half frame cut through the shadow
+            if EXPECTED_S_1GPU[name] / world * 0.5 * 1.2 + 3.0 <= left:
+                rect, full = (0, 0, H, W // 2), False
+            else:
+                out[name] = {"workload": wl["desc"], "skipped": f"time budget of the per-scene block used up ({budget_s:.0f} s); "
+                             f"a full frame takes about {EXPECTED_S_1GPU[name] / world:.0f} s on {world} GPU(s): profiles/r2_fullsize_{name}.json"}
+                continue
+        elif expect > left:
             frac = (left - 3.0) / (EXPECTED_S_1GPU[name] / world * 1.5)   # the centre rows are the expensive ones
             rows = int(H * frac) // 4 * 4
             if rows < 16:
@@ -335,8 +344,9 @@ def per_scene_block(bench, budget_s):
                  "parity": PARITY_RECORD.get(name)}
         if rect:
             entry["section"] = {"from_row": rect[0], "to_row": rect[2], "from_col": rect[1], "to_col": rect[3],
-                                "note": "centred band of rows of the full-size frame (the reference CLI's --from-row/--to-row); "
-                                        "the whole frame is recorded in profiles/r2_fullsize_%s.json" % name}
+                                "note": "section of the full-size frame (the reference CLI's --from-row/--to-row/--from-col/--to-col): the left "
+                                        "half for the Kerr-Schild scenes, a centred band of rows otherwise; the whole frame is recorded in "
+                                        "profiles/r2_fullsize_%s.json" % name}
         out[name] = entry
         bench.close_frames(r)
     return out
