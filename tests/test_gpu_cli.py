@@ -95,3 +95,34 @@ def test_blackbody_spectrum_png_matches_oracle(tmp_path):
     osc.lib().orc_tonemap(osc.dptr(xyza), H * W, abi.TONEMAP_GLOBAL_LINEAR, 1.0, osc.u8ptr(ref))
     diff = np.abs(img.reshape(-1, 3).astype(int) - ref.astype(int))
     assert diff.max() <= 1
+
+
+def test_plain_c_consumer(tmp_path):
+    """tests/c_abi_smoke.c -- C99, nothing but include/grrt.h and libgrrt.so -- renders a frame through
+    grrt_host_scene_from_toml_file -> grrt_render -> grrt_tonemap; its numbers equal the Python binding's."""
+    import torch
+    exe = str(tmp_path / "c_abi_smoke")
+    lib_dir = os.path.join(ROOT, "gr_raytracer_b200")
+    cc = subprocess.run(["cc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L", lib_dir, "-lgrrt", f"-Wl,-rpath,{lib_dir}"],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    toml = os.path.join(ROOT, "scenes", "kerr-bl.toml")
+    want = None
+    for n_dev in sorted({1, torch.cuda.device_count()}):
+        r = subprocess.run([exe, toml, ROOT, "40", "30", str(n_dev)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        tok = r.stdout.split()
+        assert tok[0] == "ok" and (int(tok[1]), int(tok[2])) == (40, 30)
+        if want is None:
+            from gr_raytracer_b200 import abi, api
+            scene = api.HostScene(toml, abi.default_cli_opts(width=40, height=30, camera_position=[-10.0, 0.0, -0.5], theta=-3.14159), ROOT)
+            with api.Context(0) as ctx:
+                out = ctx.render(scene)
+                rgb = ctx.tonemap(out["xyza"])
+            st = out["stats"]
+            want = (st["rays_base"] + st["rays_supersample"], st["accepted_steps"], float(out["xyza"][..., :3].sum(axis=-1).ravel().sum()),
+                    tuple(int(v) for v in rgb[15, 20]))
+        assert int(tok[3]) == want[0] and int(tok[4]) == want[1]
+        assert abs(float(tok[5]) - want[2]) <= 1e-9 * abs(want[2])      # same pixels, summed in a different order
+        assert tuple(int(v) for v in tok[6:9]) == want[3]
