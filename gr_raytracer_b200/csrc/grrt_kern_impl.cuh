@@ -17,6 +17,13 @@ namespace GRRT_NS {
 #ifndef GRRT_MBV
 #define GRRT_MBV 3  // resident CTAs/SM the volumetric kernels are register-allocated for
 #endif
+#ifndef GRRT_MB_KS
+#define GRRT_MB_KS 4   // Kerr-Schild: resident CTAs/SM the register allocator targets (128 registers; 3 CTAs / 168 registers
+                       // measured 8 % slower on a 640x640 frame, 5 and 6 CTAs slower still)
+#endif
+#ifndef GRRT_MBV_KS
+#define GRRT_MBV_KS 2  // ... with a VolumetricDisc in the scene
+#endif
 template <bool V>
 int launch_trace_v(const DScene& s, const TraceArgs& a, const TraceLaunch& l) {
     switch (s.geom) {
@@ -25,7 +32,7 @@ int launch_trace_v(const DScene& s, const TraceArgs& a, const TraceLaunch& l) {
         case GRRT_GEOM_SCHWARZSCHILD: return launch_trace_t<GRRT_GEOM_SCHWARZSCHILD, V, (V ? GRRT_MBV : GRRT_MB)>(s, a, l);
         case GRRT_GEOM_KERR_BL: return launch_trace_t<GRRT_GEOM_KERR_BL, V, (V ? GRRT_MBV : GRRT_MB_BL)>(s, a, l);
 #ifdef GRRT_WITH_KERR_SCHILD
-        case GRRT_GEOM_KERR: return launch_trace_t<GRRT_GEOM_KERR, V, (V ? 2 : 3)>(s, a, l);
+        case GRRT_GEOM_KERR: return launch_trace_t<GRRT_GEOM_KERR, V, (V ? GRRT_MBV_KS : GRRT_MB_KS)>(s, a, l);
 #endif
         default: return (int)cudaErrorInvalidValue;
     }

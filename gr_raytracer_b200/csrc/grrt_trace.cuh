@@ -128,6 +128,57 @@ __device__ __forceinline__ void stage_argument(const double* kcol, const double*
     }
 }
 
+#ifdef GRRT_FAST_MATH
+#define RKCH(j) c_rk_ch[j]
+#define RKCT(j) c_rk_ct[j]
+#else
+#define RKCH(j) rk_ch(j)
+#define RKCT(j) rk_ct(j)
+#endif
+// Argument of the last stage AND, from the same five shared-memory loads per component, the sums y + CH1 k1 + ... + CH5 k5
+// and CT1 k1 + ... + CT5 k5 of the stored components (left to right, as runge_kutta.rs:115-123 forms them once all six k
+// exist): the 5th-order solution and the error vector of those components then need no registers while stages 1..5
+// run -- they are completed with k6 after the last right-hand side.
+template <int G>
+__device__ __forceinline__ void stage_argument_final(const double* kcol, const double* y, double* tmp, double* y_new, double* acc_e) {
+    constexpr int NC = Comp<G>::count;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (!Comp<G>::stored(i)) {
+            tmp[i] = y[i];
+            continue;
+        }
+        double k[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) k[j] = kcol[(j * NC + Comp<G>::slot(i)) * kTraceThreads];
+        double acc;
+#if defined(GRRT_SINCOS_DELTA) && defined(GRRT_FAST_MATH)
+        if (i == 2 && GeomTraits<G>::chart != CH_CART) {
+            acc = RKB(5, 0) * k[0];
+#pragma unroll
+            for (int j = 1; j < 5; ++j) acc = acc + RKB(5, j) * k[j];
+        } else
+#endif
+        {
+            acc = y[i];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) acc = acc + RKB(5, j) * k[j];
+        }
+        tmp[i] = acc;
+        double yn = y[i], ae = 0.0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+#ifdef GRRT_FAST_MATH
+            if (j == 1) continue;   // CH2 = CT2 = 0
+#endif
+            yn = yn + RKCH(j) * k[j];
+            ae = ae + RKCT(j) * k[j];
+        }
+        y_new[i] = yn;
+        acc_e[i] = ae;
+    }
+}
+
 struct RayCtx {  // per-lane ray bookkeeping kept in registers
     unsigned long long unit;
     unsigned step;
@@ -522,6 +573,9 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 double acc_e[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
+#ifdef GRRT_DEFER_SUMS
+                    if (Comp<G>::stored(i)) continue;   // formed at the last stage from the stored k1..k5
+#endif
                     y_new[i] = y[i];
                     acc_e[i] = 0.0;
                 }
@@ -546,7 +600,11 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                         case 2: stage_argument<G, 2>(kcol, y, tmp); break;
                         case 3: stage_argument<G, 3>(kcol, y, tmp); break;
                         case 4: stage_argument<G, 4>(kcol, y, tmp); break;
+#ifdef GRRT_DEFER_SUMS
+                        default: stage_argument_final<G>(kcol, y, tmp, y_new, acc_e); break;
+#else
                         default: stage_argument<G, 5>(kcol, y, tmp); break;
+#endif
                     }
                     double d[8];
 #if defined(GRRT_SINCOS_DELTA) && defined(GRRT_FAST_MATH)
@@ -584,6 +642,9 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                         if (Comp<G>::on(i)) {
                             const double k = h_cur * d[i];
                             if (s < 5 && Comp<G>::stored(i)) kst[Comp<G>::slot(i) * kTraceThreads] = k;
+#ifdef GRRT_DEFER_SUMS
+                            if (s < 5 && Comp<G>::stored(i)) continue;   // summed at the last stage (stage_argument_final)
+#endif
 #ifdef GRRT_FAST_MATH
                             // CH2 = CT2 = 0 (runge_kutta.rs:43-55): the exact build adds the zeros; skipping them is worth
                             // 3 % for Schwarzschild (C1 382 -> 370 ms) but costs KerrBL 7 % (register allocation at 96)

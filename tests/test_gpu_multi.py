@@ -13,10 +13,6 @@ from helpers import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _skip_without_two_gpus():
-    return pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-
-
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 @pytest.mark.parametrize("p2p", ["1", "0"])
 def test_two_rank_frame_is_bit_identical(p2p):
@@ -27,6 +23,7 @@ def test_two_rank_frame_is_bit_identical(p2p):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("bit-identical to 1-GPU frame: True") == 2
     assert ("peer-store path" in r.stdout) == (p2p == "1")
+    assert r.stdout.count("is intact and B is right: True") == 3     # back-to-back frames do not race
 
 
 def _frames_equal(a, b):

@@ -26,5 +26,30 @@ for name, w, h in (("C2", 301, 203), ("C1", 96, 64)):
         print('  peer-store path' if fr.p2p else '  all-gather path', flush=True)
     fr.close()
     eng.close()
+# back-to-back frames with different cameras: rank 0 copies frame A out asynchronously while the other ranks are
+# already tracing frame B -- the peers must not store frame B's pixels into rank 0's buffers before the copy of A has run
+sc = api.HostScene(os.path.join(ROOT, CONFIGS["C2"]['toml']), config_opts("C2", width=301, height=203), ROOT)
+eng = DeviceEngine(ctx, sc)
+fr = FrameRenderer(eng, sc.c.adaptive, 301, 203, rank, world)
+for trial in range(3):
+    sc.set_camera(camera_position=(-10.0, 0.0, -0.5))
+    ctx.set_camera(eng.dscene, sc.c.camera)
+    fr.render()
+    host_a = torch.empty(fr.xyza.shape, dtype=fr.xyza.dtype).pin_memory()
+    host_a.copy_(fr.xyza, non_blocking=True)          # no synchronisation before the next frame starts
+    sc.set_camera(camera_position=(-8.0, 3.0, 1.0))
+    ctx.set_camera(eng.dscene, sc.c.camera)
+    fr.render()
+    torch.cuda.synchronize()
+    if rank == 0:
+        got_b = fr.xyza.cpu().numpy().reshape(203, 301, 4)
+        ref_b = ctx.render(sc)["xyza"]
+        sc.set_camera(camera_position=(-10.0, 0.0, -0.5))
+        ref_a = ctx.render(sc)["xyza"]
+        ok = np.array_equal(host_a.numpy().reshape(203, 301, 4), ref_a) and np.array_equal(got_b, ref_b)
+        print(f"back-to-back frames, trial {trial}: frame A read while frame B renders is intact and B is right: {ok}", flush=True)
+        assert ok
+fr.close()
+eng.close()
 dist.barrier()
 dist.destroy_process_group()
