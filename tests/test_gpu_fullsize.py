@@ -53,9 +53,9 @@ def _impact_parameters(sc, rows, cols):
 
 
 def _oracle_full_frame(name, sc):
-    """The oracle's full-resolution 1-spp frame (C1 ~2 min, C2 ~1 min of all host cores), cached in gpurun_out/ for
-    the other tests of this session."""
-    cache = os.path.join(ROOT, "gpurun_out", f"oracle_full_{name}.npz")
+    """The oracle's full-resolution 1-spp frame (C1 ~2 min, C2 ~1 min of all host cores), cached under $GRRT_TEST_CACHE
+    (default /tmp/grrt_test_cache) for later runs on the same box."""
+    cache = os.path.join(os.environ.get("GRRT_TEST_CACHE", "/tmp/grrt_test_cache"), f"oracle_full_{name}.npz")
     if os.path.exists(cache):
         z = np.load(cache)
         return {k: z[k] for k in ("xyza", "stop", "ray_class", "steps")}, int(z["ray_errors"])

@@ -50,7 +50,7 @@ def rel_err(a, b):
     return np.where(scale > 0, err / np.maximum(scale, 1e-300), err)
 
 
-def run(name, n_samples=300, n_long=30, width=None, height=None, seed=2026, ctx=None, verbose=True, adaptive=True):
+def run(name, n_samples=300, n_long=30, width=None, height=None, seed=2026, ctx=None, verbose=True, adaptive=True, devices=1):
     from gr_raytracer_b200 import abi, api
     from oracle import scene as osc
     from helpers import CONFIGS, config_opts
@@ -67,7 +67,7 @@ def run(name, n_samples=300, n_long=30, width=None, height=None, seed=2026, ctx=
     scene = api.HostScene(toml, opts, ROOT, is_text=is_text)
     own = ctx is None
     if own:
-        ctx = api.Context(0)
+        ctx = api.Context(0) if devices <= 1 else api.Context(list(range(devices)))   # one multi-device context (grrt_init_multi)
     t0 = time.perf_counter()
     dev = ctx.render(scene)
     wall = time.perf_counter() - t0
@@ -124,7 +124,7 @@ def run(name, n_samples=300, n_long=30, width=None, height=None, seed=2026, ctx=
             err[idx] = e2
     bad = np.flatnonzero(~ok)
     res = {
-        "config": name, "adaptive": bool(adaptive), "width": W, "height": H, "wall_s": wall, "device_ms_total": st["device_ms_total"],
+        "config": name, "adaptive": bool(adaptive), "devices": ctx.device_count, "width": W, "height": H, "wall_s": wall, "device_ms_total": st["device_ms_total"],
         "device_ms_base": st["device_ms_base"], "device_ms_supersample": st["device_ms_supersample"],
         "rays_base": st["rays_base"], "rays_supersample": st["rays_supersample"], "pixels_supersampled": st["pixels_supersampled"],
         "accepted_steps": st["accepted_steps"], "attempts": st["attempts"], "raymarch_samples": st["raymarch_samples"],
@@ -165,8 +165,9 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--save-steps", default=None, help="write the per-pixel step counts and stop reasons (npz)")
     ap.add_argument("--base-only", action="store_true", help="1-spp pass only (adaptive supersampling off)")
+    ap.add_argument("--devices", type=int, default=1, help="render through one multi-device context over this many GPUs")
     a = ap.parse_args()
-    res, dev = run(a.config, a.samples, a.long, a.width, a.height, adaptive=not a.base_only)
+    res, dev = run(a.config, a.samples, a.long, a.width, a.height, adaptive=not a.base_only, devices=a.devices)
     if a.out:
         os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
         with open(a.out, "w") as f:
