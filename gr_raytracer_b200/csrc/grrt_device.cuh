@@ -90,6 +90,9 @@ GD void sincos_pi2(double x, double* sn, double* cs) {
     *cs = ((k + 1) & 2) ? -b : b;
 }
 
+// the same routine as a call, for rare paths inside straight-line hot code
+__device__ __noinline__ void sincos_cold(double x, double* sn, double* cs) { sincos_pi2(x, sn, cs); }
+
 // Rust semantics
 GD double rclamp(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 GD bool in01(double t) { return t >= 0.0 && t <= 1.0; }

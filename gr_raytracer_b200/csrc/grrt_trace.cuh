@@ -98,7 +98,7 @@ __host__ __device__ constexpr double rk_ct(int s) {
 }
 // argument of stage SS: y + B_s1 k1 + B_s2 k2 + ... summed left to right (runge_kutta.rs:95-124); straight-line so
 // that all shared-memory loads of a stage are issued together and the coefficients are instruction operands
-#if defined(GRRT_FAST_MATH) && defined(GRRT_UNROLL_STAGES)
+#if defined(GRRT_FAST_MATH) && (defined(GRRT_UNROLL_STAGES) || defined(GRRT_RKB_CONST))
 #define RKB(SS, j) c_rk_b[((SS) - 1) * 5 + (j)]
 #else
 #define RKB(SS, j) rk_b(SS, j)
@@ -625,7 +625,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                                 st = fma(sin0, cd, cos0 * sd);
                                 ct = fma(cos0, cd, -(sin0 * sd));
                             } else {
-                                sincos_pi2(y[2] + delta, &st, &ct);
+                                sincos_cold(y[2] + delta, &st, &ct);   // out of line: keeps the straight-line stage code dense
                             }
                         }
                         geodesic_rhs_trig<G>(S, C, tmp, st, ct, d);
