@@ -550,6 +550,19 @@ static int scene_upload_one(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene**
         d.radius = o.radius;
         d.center_norm = std::sqrt(o.position[0] * o.position[0] + o.position[1] * o.position[1] + o.position[2] * o.position[2]);
         d.axis_is_z = (o.axis[0] == 0.0 && o.axis[1] == 0.0 && o.axis[2] == 1.0) ? 1 : 0;
+        // summary for segment_needs_cartesian() (grrt_device.cuh)
+        if (o.kind == GRRT_OBJ_DISC) {
+            s.pre_flags |= PRE_HAS_DISC;
+        } else if (o.kind == GRRT_OBJ_SPHERE) {
+            const double Rs = o.radius * (1.0 + 1e-9) + 1e-300;
+            const double far = d.center_norm + Rs, near = d.center_norm - Rs;
+            s.pre_sph_far2[s.pre_n_spheres] = far * far * (1.0 + 1e-12);
+            s.pre_sph_near2[s.pre_n_spheres] = near > 0.0 ? near * near * (1.0 - 1e-12) : -1.0;
+            ++s.pre_n_spheres;
+        } else {
+            s.pre_flags |= d.axis_is_z ? PRE_HAS_VOL : PRE_ALWAYS;
+            s.pre_vol_h = std::max(s.pre_vol_h, 3.0 * o.thickness * (1.0 + 1e-9));
+        }
         d.sphere_temperature = o.sphere_temperature;
         d.r_in = o.inner_radius;
         d.r_out = o.outer_radius;

@@ -623,27 +623,25 @@ GD bool segment_needs_cartesian(const DScene& S, double r0, double th0, double r
     const double lo = 1e-9, hi = kPi - 1e-9;
     if (!(th0 > lo && th0 < hi && th1 > lo && th1 < hi && r0 > 0.0 && r1 > 0.0)) return true;
     const double aa = (GeomTraits<G>::chart == CH_BL) ? S.a * S.a : 0.0;
-    if (!(r1 * r1 + aa < S.max_radius_sq * (1.0 - 1e-12))) return true;  // may have escaped: evaluate exactly
-    const double s0 = th0 - 0.5 * kPi, s1 = th1 - 0.5 * kPi;               // sign(z) = -sign(s)
-    const bool same_side = (s0 > 0.0) == (s1 > 0.0);
-    for (int k = 0; k < S.n_objects; ++k) {
-        const DObject& o = S.obj[k];
-        if (o.kind == GRRT_OBJ_DISC) {
-            if (!(same_side && fabs(s0) > 1e-9 && fabs(s1) > 1e-9)) return true;
-        } else if (o.kind == GRRT_OBJ_SPHERE) {
-            // |x| lies in [r, sqrt(r^2 + a^2)]; compared as squares so that no square root is needed
-            const double Rs = o.radius * (1.0 + 1e-9) + 1e-300;
-            const double far = o.center_norm + Rs, near = o.center_norm - Rs;
-            const double far2 = far * far * (1.0 + 1e-12), near2 = near * near * (1.0 - 1e-12);
-            const double q0 = r0 * r0, q1 = r1 * r1;
-            const bool out0 = q0 > far2 || (near > 0.0 && q0 + aa < near2);
-            const bool out1 = q1 > far2 || (near > 0.0 && q1 + aa < near2);
-            if (!(out0 && out1)) return true;
-        } else {
-            const double H = 3.0 * o.thickness * (1.0 + 1e-9);
-            const double c = 2.0 / kPi;
-            if (!(o.axis_is_z && same_side && r0 * c * fabs(s0) > H && r1 * c * fabs(s1) > H)) return true;
+    const double q0 = r0 * r0, q1 = r1 * r1;
+    if (!(q1 + aa < S.max_radius_sq * (1.0 - 1e-12))) return true;  // may have escaped: evaluate exactly
+    const double s0 = th0 - 0.5 * kPi, s1 = th1 - 0.5 * kPi;        // sign(z) = -sign(s)
+    const int flags = S.pre_flags;   // the per-object conditions of the comment above, and-ed over the objects at upload
+    if (flags & PRE_ALWAYS) return true;
+    if (flags & (PRE_HAS_DISC | PRE_HAS_VOL)) {
+        if ((s0 > 0.0) != (s1 > 0.0)) return true;
+        if ((flags & PRE_HAS_DISC) && !(fabs(s0) > 1e-9 && fabs(s1) > 1e-9)) return true;
+        if (flags & PRE_HAS_VOL) {
+            const double c = 2.0 / kPi, H = S.pre_vol_h;
+            if (!(r0 * c * fabs(s0) > H && r1 * c * fabs(s1) > H)) return true;
         }
+    }
+    for (int k = 0; k < S.pre_n_spheres; ++k) {
+        // |x| lies in [r, sqrt(r^2 + a^2)]; compared as squares so that no square root is needed
+        const double far2 = S.pre_sph_far2[k], near2 = S.pre_sph_near2[k];
+        const bool out0 = q0 > far2 || q0 + aa < near2;
+        const bool out1 = q1 > far2 || q1 + aa < near2;
+        if (!(out0 && out1)) return true;
     }
     return false;
 }

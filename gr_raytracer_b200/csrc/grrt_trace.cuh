@@ -429,7 +429,9 @@ enum { ST_IDLE = 0, ST_ACTIVE = 1, ST_DEAD = 2 };
 #ifdef GRRT_FAST_MATH
 // The step-size controller's exact path is cold in the fast build (seed out of range, err = 0 / inf / NaN): kept out
 // of line so that the attempt loop stays short.
-__device__ __noinline__ double controller_pow_cold(double x) { return pow_glibc(pow_tables_global(), x, 1.0 / 5.0); }
+__device__ __noinline__ double controller_pow_cold(double epsilon, double err) {
+    return pow_glibc(pow_tables_global(), epsilon / err, 1.0 / 5.0);
+}
 #endif
 
 // the exact build keeps the glibc-compatible pow tables in shared memory (one pow per attempt); the fast build only
@@ -692,7 +694,7 @@ trace_kernel(const __grid_constant__ DScene S, const __grid_constant__ TraceArgs
                 } else
 #endif
 #ifdef GRRT_FAST_MATH
-                if (err > 0.0) h_proposed = 0.9 * h_cur * controller_pow_cold(S.epsilon / err);
+                if (err > 0.0) h_proposed = 0.9 * h_cur * controller_pow_cold(S.epsilon, err);
 #else
                 if (err > 0.0) h_proposed = 0.9 * h_cur * pow_glibc(pow_tab, S.epsilon / err, 1.0 / 5.0);
 #endif

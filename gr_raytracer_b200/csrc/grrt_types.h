@@ -64,8 +64,15 @@ struct DScene {
     uint32_t bb_n;
     uint32_t n_vol;          // number of VolumetricDisc objects
     const double* srgb_lut;  // 256 entries: inv_compand_srgb(i/255) (color.rs:301-308), built on the host
+    // summary of the objects for segment_needs_cartesian() (spherical / Boyer-Lindquist charts), built at upload:
+    // straight-line tests instead of a loop over the objects with a switch on their kind
+    int pre_flags;           // PRE_* bits
+    int pre_n_spheres;
+    double pre_vol_h;        // largest capture half-height 3 thickness (1 + 1e-9) of the VolumetricDiscs
+    double pre_sph_far2[GRRT_MAX_OBJECTS], pre_sph_near2[GRRT_MAX_OBJECTS];   // near2 < 0: the sphere contains the origin
     DObject obj[GRRT_MAX_OBJECTS];
 };
+enum { PRE_HAS_DISC = 1, PRE_HAS_VOL = 2, PRE_ALWAYS = 4 /* a VolumetricDisc with a tilted axis: no cheap rejection */ };
 
 enum { CNT_ATTEMPTS = 0, CNT_ACCEPTED = 1, CNT_SAMPLES = 2, CNT_ERRORS = 3, CNT_OVERFLOW = 4, CNT_RAYS = 5,
        CNT_STOP0 = 8 /* 8..13 */ };
