@@ -90,6 +90,30 @@ GD void sincos_pi2(double x, double* sn, double* cs) {
     *cs = ((k + 1) & 2) ? -b : b;
 }
 
+// libm routines used by the event code (shading, chart conversions, the ray-march) as calls: CUDA inlines pow (~250
+// instructions), exp, atan2, log10 and the Payne-Hanek sincos at every call site, which made the ray-march loop 4200
+// instructions (67 KB) -- far beyond the instruction caches, and it is streamed once per block of 32 samples.  One shared
+// body per routine keeps that code resident.  Same routines, same results.
+#ifndef GRRT_NO_LIBM_CALLS
+__device__ __noinline__ double m_pow(double a, double b) { return pow(a, b); }
+__device__ __noinline__ double m_exp(double a) { return exp(a); }
+__device__ __noinline__ double m_atan2(double a, double b) { return atan2(a, b); }
+__device__ __noinline__ double m_log10(double a) { return log10(a); }
+__device__ __noinline__ double m_acos(double a) { return acos(a); }
+__device__ __noinline__ void m_sincos(double x, double* sn, double* cs) { sincos(x, sn, cs); }
+__device__ __noinline__ double m_sin(double a) { return sin(a); }
+__device__ __noinline__ double m_cos(double a) { return cos(a); }
+#else
+#define m_sin sin
+#define m_cos cos
+#define m_pow pow
+#define m_exp exp
+#define m_atan2 atan2
+#define m_log10 log10
+#define m_acos acos
+#define m_sincos sincos
+#endif
+
 // the same routine as a call, for rare paths inside straight-line hot code
 __device__ __noinline__ void sincos_cold(double x, double* sn, double* cs) { sincos_pi2(x, sn, cs); }
 
@@ -227,7 +251,7 @@ GD double bl_inner(const BlMetric& g, const double v[4], const double w[4]) {
 GD double co_angular_velocity(double r_s, double a, double r) {
     double m = 0.5 * r_s;
     double sqrt_m = sqrt(m);
-    return sqrt_m / (pow(r, 1.5) + a * sqrt_m);
+    return sqrt_m / (m_pow(r, 1.5) + a * sqrt_m);
 }
 GD bool co_killing(double r_s, double a, double r, double& u_t, double& u_phi) {
     double omega = co_angular_velocity(r_s, a, r);
@@ -260,16 +284,16 @@ GD void cartesian_to_spherical(double x, double y, double z, double& r, double& 
         phi = 0.0;
         return;
     }
-    theta = acos(z / r);
-    phi = atan2(y, x);
+    theta = m_acos(z / r);
+    phi = m_atan2(y, x);
 }
 GD void cartesian_to_bl(double a, double x, double y, double z, double& r, double& theta, double& phi) {
     double rho_sqr = x * x + y * y + z * z;
     double w = rho_sqr - a * a;
     double r_sqr = 0.5 * (w + sqrt(w * w + 4.0 * a * a * z * z));
     r = sqrt(r_sqr);
-    theta = (r == 0.0) ? 0.0 : acos(rclamp(z / r, -1.0, 1.0));
-    phi = atan2(r * y - a * x, r * x + a * y);
+    theta = (r == 0.0) ? 0.0 : m_acos(rclamp(z / r, -1.0, 1.0));
+    phi = m_atan2(r * y - a * x, r * x + a * y);
 }
 // native position -> Cartesian embedding (point.rs:140-155, spherical_coordinates_helper.rs:28-39)
 template <int G>
@@ -302,10 +326,10 @@ GD double inner_product(const DScene& S, const double* pos, const double* v, con
     if (G == GRRT_GEOM_EUCLIDEAN) {
         return 1.0 * v[0] * w[0] + -v[1] * w[1] + -v[2] * w[2] + -v[3] * w[3];
     } else if (G == GRRT_GEOM_EUCLIDEAN_SPHERICAL) {
-        double r = pos[1], s = sin(pos[2]);
+        double r = pos[1], s = m_sin(pos[2]);
         return 1.0 * v[0] * w[0] - v[1] * w[1] - r * r * v[2] * w[2] - r * r * s * s * v[3] * w[3];
     } else if (G == GRRT_GEOM_SCHWARZSCHILD) {
-        double r = pos[1], s = sin(pos[2]);
+        double r = pos[1], s = m_sin(pos[2]);
         double a = 1.0 - S.radius / r;
         return a * v[0] * w[0] - v[1] * w[1] / a - r * r * v[2] * w[2] - r * r * s * s * v[3] * w[3];
     } else if (G == GRRT_GEOM_KERR) {
@@ -315,7 +339,7 @@ GD double inner_product(const DScene& S, const double* pos, const double* v, con
         return vt_m_w(v, m, w);
     } else {
         double st, ct;
-        sincos(pos[2], &st, &ct);
+        m_sincos(pos[2], &st, &ct);
         BlMetric g = bl_metric(S.radius, S.a, pos[1], st, ct);
         return bl_inner(g, v, w);
     }
@@ -336,7 +360,7 @@ GD void stationary_velocity(const DScene& S, const double* pos, double u[4]) {
         KsFK k = ks_f_k(S.radius, S.a, pos[1], pos[2], pos[3]);
         u[0] = 1.0 / sqrt(1.0 - k.f);
     } else if (G == GRRT_GEOM_KERR_BL) {
-        double c = cos(pos[2]);
+        double c = m_cos(pos[2]);
         double sig = pos[1] * pos[1] + S.a * S.a * (c * c);
         u[0] = 1.0 / sqrt(1.0 - S.radius * pos[1] / sig);
     } else {
@@ -555,7 +579,7 @@ GD void momentum_from_state(const DScene& S, const RayConst& C, const double* y,
     } else if (G == GRRT_GEOM_KERR_BL) {  // kerr_bl.rs:225-249
         double r = y[1], a = S.a;
         double st, ct;
-        sincos(y[2], &st, &ct);
+        m_sincos(y[2], &st, &ct);
         double del = bl_delta(r, S.radius, a);
         double sig = r * r + a * a * (ct * ct);
         double sin2 = st * st;
@@ -744,7 +768,7 @@ GD Cie blend(Cie self, Cie other) {  // color.rs:49-69
     return cie(x, y, z, ao);
 }
 GD Cie apply_beaming(Cie c, double redshift, double beaming) {  // color.rs:72-80
-    double f = pow(redshift, beaming);
+    double f = m_pow(redshift, beaming);
     return cie(c.x * f, c.y * f, c.z * f, c.a);
 }
 GD Cie texel_xyz(const DScene& S, const DTexture& t, uint32_t x, uint32_t y) {  // color.rs:32-40, 310-332
@@ -785,7 +809,7 @@ GD Cie sample_blackbody(const DScene& S, double temperature) {  // texture.rs:14
     if (n == 0) return cie(0.0, 0.0, 0.0, 1.0);
     const double* lt = S.bb_log_t;
     const double* c = S.bb_xyz;
-    double log_t = log10(fmax(temperature, 10.0));
+    double log_t = m_log10(fmax(temperature, 10.0));
     uint32_t lastk = n - 1;
     if (!isfinite(log_t) || log_t <= __ldg(lt)) return cie(__ldg(c), __ldg(c + 1), __ldg(c + 2), 1.0);
     if (log_t >= __ldg(lt + lastk)) return cie(__ldg(c + 3 * lastk), __ldg(c + 3 * lastk + 1), __ldg(c + 3 * lastk + 2), 1.0);
@@ -846,10 +870,10 @@ GD bool disc_intersects(const DObject& o, V3 ys, V3 ye, Hit& h) {  // disc.rs:41
     V3 ip = ys + t * d;
     double rr = dot3(ip, ip);
     if (rr >= o.r_in * o.r_in && rr <= o.r_out * o.r_out) {
-        double phi = atan2(ip.y - 0.0, ip.x - 0.0);
+        double phi = m_atan2(ip.y - 0.0, ip.x - 0.0);
         double r = (sqrt(rr) - o.r_in) / (o.r_out - o.r_in);
         double sp, cp;
-        sincos(phi, &sp, &cp);
+        m_sincos(phi, &sp, &cp);
         h.u = 0.5 + 0.5 * r * cp;
         h.v = 0.5 + 0.5 * r * sp;
         h.point = ip;
@@ -975,10 +999,10 @@ GD bool vol_first_hit(const DObject& o, V3 from, V3 to, double& t_sel) {
 GD void vol_get_uv(const DObject& o, V3 p, double& u, double& v) {  // :140-152
     double x = dot3(p, v3(o.e1[0], o.e1[1], o.e1[2])), y = dot3(p, v3(o.e2[0], o.e2[1], o.e2[2]));
     double rr = sqrt(x * x + y * y);
-    double phi = atan2(y, x);
+    double phi = m_atan2(y, x);
     double r = (rr - o.r_in) / (o.r_out - o.r_in);
     double sp, cp;
-    sincos(phi, &sp, &cp);
+    m_sincos(phi, &sp, &cp);
     u = 0.5 + 0.5 * r * cp;
     v = 0.5 + 0.5 * r * sp;
 }
@@ -1042,17 +1066,17 @@ GD double vol_density(const DObject& o, const uint8_t* perm, V3 p) {  // :97-138
     double r = norm3(cross3(p, axis));
     if (r <= o.r_in || r >= o.r_out) return 0.0;
     double ht = h / o.thickness;
-    double vertical_falloff = exp(-(ht * ht));
+    double vertical_falloff = m_exp(-(ht * ht));
     if (vertical_falloff < 0.001) return 0.0;
-    double radial_base = pow(o.r_in / r, 1.5);
+    double radial_base = m_pow(o.r_in / r, 1.5);
     double boundary_falloff = 1.0;
     double d1 = o.r_out - r, d2 = r - o.r_in;
-    boundary_falloff *= exp(-1.0 / fmax(d1 * d1, 0.0001));
-    boundary_falloff *= exp(-1.0 / fmax(d2 * d2, 0.0001));
+    boundary_falloff *= m_exp(-1.0 / fmax(d1 * d1, 0.0001));
+    boundary_falloff *= m_exp(-1.0 / fmax(d2 * d2, 0.0001));
     double x_local = dot3(p, v3(o.e1[0], o.e1[1], o.e1[2])), y_local = dot3(p, v3(o.e2[0], o.e2[1], o.e2[2]));
-    double phi = atan2(y_local, x_local);
+    double phi = m_atan2(y_local, x_local);
     double sphi, cphi;
-    sincos(phi, &sphi, &cphi);
+    m_sincos(phi, &sphi, &cphi);
     double npx = r * o.noise_scale[0], npy = cphi * o.noise_scale[1], npz = sphi * o.noise_scale[1];
     // fbm(noise_p, 0.5) (:330-342): g = exp2(-0.5)
     const double g = 0.70710678118654757;

@@ -220,7 +220,7 @@ GD void init_ray(const DScene& S, const double pos[4], const double mom[4], doub
     if (G == GRRT_GEOM_KERR_BL) {  // kerr_bl.rs:505-577 (BL branch), 176-223
         double r = pos[1];
         double st, ct;
-        sincos(pos[2], &st, &ct);
+        m_sincos(pos[2], &st, &ct);
         BlMetric g = bl_metric(S.radius, S.a, r, st, ct);
         // p_cov = g * p with nalgebra's accumulation (zero entries kept)
         double pc0 = ((g.tt * mom[0] + 0.0 * mom[1]) + 0.0 * mom[2]) + g.tph * mom[3];
@@ -345,7 +345,7 @@ __device__ __forceinline__ Cie vol_march_warp(const DScene& S, const DObject& o,
         bool emit = false;
         int terr = 0;
         if (has) {
-            att = exp(-d_s * density * sigma);
+            att = m_exp(-d_s * density * sigma);
             double u_t, u_phi;
             if (orbit_coefficients_cart<G>(S, p, u_t, u_phi)) {
                 double emitter_energy = u_t * p_t + u_phi * p_phi;
@@ -357,7 +357,7 @@ __device__ __forceinline__ Cie vol_march_warp(const DScene& S, const DObject& o,
                     double u, v;
                     vol_get_uv(o, p, u, v);
                     light = texture_color(S, o.tex, u, v, temperature, redshift);
-                    light_att = exp(-density * d_s * sigma);
+                    light_att = m_exp(-density * d_s * sigma);
                     double tr = temperature / o.bref_temperature;
                     double tr2 = tr * tr;
                     intensity = tr2 * tr2;
