@@ -41,6 +41,7 @@ struct GrrtCtx {
 struct GrrtDeviceScene {
     DScene s;
     std::vector<void*> allocs;
+    std::vector<size_t> alloc_bytes;   // parallel to allocs
     GrrtAdaptive adaptive;
     bool has_vol = false;
     std::vector<GrrtDeviceScene*> replicas;  // multi-device context: the same scene on members[k]'s device
@@ -74,6 +75,7 @@ int upload(GrrtCtx* ctx, GrrtDeviceScene* ds, const T* host, size_t count, const
     void* p = nullptr;
     CUDA_TRY(ctx, cudaMallocAsync(&p, count * sizeof(T), ctx->stream));
     ds->allocs.push_back(p);
+    ds->alloc_bytes.push_back(count * sizeof(T));
     CUDA_TRY(ctx, cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     *out = static_cast<const T*>(p);
     return GRRT_OK;
@@ -313,6 +315,8 @@ struct DevBuf {
 
 }  // namespace
 
+static void preload_small_kernels(GrrtCtx* ctx);
+
 // =========================================================================================================
 extern "C" {
 
@@ -352,6 +356,10 @@ static int init_one(int device_id, GrrtCtx** out) {
         grrt_destroy(ctx);
         return GRRT_ERR_CUDA;
     }
+    // CUDA loads a kernel's code on its first launch on a device, and that load waits for the kernels already running
+    // there: with several devices driven from one thread the first frame would trace its passes one device after the
+    // other.  Launch the small kernels once with no work now.
+    preload_small_kernels(ctx);
     *out = ctx;
     return GRRT_OK;
 }
@@ -469,13 +477,68 @@ int grrt_scene_set_camera(GrrtCtx* ctx, GrrtDeviceScene* ds, const GrrtCamera* c
 
 static int scene_upload_one(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out);
 
+// The scene of the primary device copied to a member device: the tables travel device to device over NVLink (one
+// host -> device transfer per frame, not one per GPU), the parameter block is patched to the member's copies.
+static int scene_replicate(GrrtCtx* ctx, const GrrtDeviceScene* src, GrrtCtx* m, GrrtDeviceScene** out) {
+    *out = nullptr;
+    GrrtDeviceScene* r = new GrrtDeviceScene();
+    r->s = src->s;
+    r->adaptive = src->adaptive;
+    r->has_vol = src->has_vol;
+    auto bail = [&](GrrtCtx* c, const char* what) {
+        m->last_error = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
+        grrt_scene_free(c, r);
+        return GRRT_ERR_CUDA;
+    };
+    cudaEvent_t uploaded;   // the primary's host -> device copies are complete
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming) != cudaSuccess)
+        return bail(m, "cudaEventCreate");
+    cudaEventRecord(uploaded, ctx->stream);
+    if (cudaSetDevice(m->device) != cudaSuccess) { cudaEventDestroy(uploaded); return bail(m, "cudaSetDevice"); }
+    cudaStreamWaitEvent(m->stream, uploaded, 0);
+    std::vector<void*> copy(src->allocs.size(), nullptr);
+    for (size_t k = 0; k < src->allocs.size(); ++k) {
+        void* p = nullptr;
+        if (cudaMallocAsync(&p, src->alloc_bytes[k], m->stream) != cudaSuccess) { cudaEventDestroy(uploaded); return bail(m, "cudaMallocAsync"); }
+        r->allocs.push_back(p);
+        r->alloc_bytes.push_back(src->alloc_bytes[k]);
+        copy[k] = p;
+        if (cudaMemcpyPeerAsync(p, m->device, src->allocs[k], ctx->device, src->alloc_bytes[k], m->stream) != cudaSuccess) {
+            cudaEventDestroy(uploaded);
+            return bail(m, "cudaMemcpyPeerAsync");
+        }
+    }
+    cudaSetDevice(ctx->device);
+    cudaEventDestroy(uploaded);   // released once the recorded work has completed
+    auto patch = [&](const void* p) -> const void* {
+        if (!p) return p;
+        for (size_t k = 0; k < src->allocs.size(); ++k)
+            if (p == src->allocs[k]) return copy[k];
+        return p;
+    };
+    DScene& s = r->s;
+    s.srgb_lut = m->d_srgb_lut;
+    s.celestial.rgba = static_cast<const uint8_t*>(patch(s.celestial.rgba));
+    s.bb_log_t = static_cast<const double*>(patch(s.bb_log_t));
+    s.bb_xyz = static_cast<const double*>(patch(s.bb_xyz));
+    for (int k = 0; k < GRRT_MAX_OBJECTS; ++k) {
+        DObject& o = s.obj[k];
+        o.tex.rgba = static_cast<const uint8_t*>(patch(o.tex.rgba));
+        o.temp.lut_r = static_cast<const double*>(patch(o.temp.lut_r));
+        o.temp.lut_t = static_cast<const double*>(patch(o.temp.lut_t));
+        o.perm = static_cast<const uint8_t*>(patch(o.perm));
+    }
+    *out = r;
+    return GRRT_OK;
+}
+
 int grrt_scene_upload(GrrtCtx* ctx, const GrrtScene* sc, GrrtDeviceScene** out) {
     if (!ctx || !sc || !out) return GRRT_ERR_INVALID_ARGUMENT;
     int rc = scene_upload_one(ctx, sc, out);
     if (rc) return rc;
     for (GrrtCtx* m : ctx->members) {  // the same scene on every device of a multi-device context
         GrrtDeviceScene* r = nullptr;
-        rc = scene_upload_one(m, sc, &r);
+        rc = scene_replicate(ctx, *out, m, &r);
         if (rc) {
             ctx->last_error = m->last_error;
             grrt_scene_free(ctx, *out);
@@ -1246,3 +1309,20 @@ int grrt_measure_fp64_peak(GrrtCtx* ctx, double* dfma_per_second, double* ms_out
 }
 
 }  // extern "C"
+
+namespace {
+__global__ void cost_keys_kernel(const uint32_t* sel, uint32_t n, const uint32_t* steps, uint32_t* keys);
+}
+// forces the code of the small kernels onto the context's device (an attribute query loads a lazily loaded function)
+static void preload_small_kernels(GrrtCtx* ctx) {
+    cudaSetDevice(ctx->device);
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, luminance_keys_kernel);
+    cudaFuncGetAttributes(&a, mask_flags_kernel);
+    cudaFuncGetAttributes(&a, fill_mask_color_kernel);
+    cudaFuncGetAttributes(&a, linear_max_kernel);
+    cudaFuncGetAttributes(&a, tonemap_kernel);
+    cudaFuncGetAttributes(&a, grrt_exact_resolve);
+    cudaFuncGetAttributes(&a, cost_keys_kernel);
+    cudaGetLastError();
+}
