@@ -21,6 +21,9 @@ struct GrrtCtx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // device -> host copy of the base frame while the supersampling pass runs
+    void* h_stage = nullptr;               // pinned staging for the supersampled pixels (ids + values)
+    size_t h_stage_bytes = 0;
     std::string last_error;
     double* d_srgb_lut = nullptr;
     unsigned long long* d_queue = nullptr;     // work-queue counter
@@ -339,7 +342,8 @@ static int init_one(int device_id, GrrtCtx** out) {
     }
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* e = std::getenv("GRRT_FMA")) ctx->use_fma = !(e[0] == '0');
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GRRT_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GRRT_ERR_CUDA; }
     {  // keep freed blocks cached in the device's default memory pool instead of returning them to the OS
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
@@ -430,6 +434,8 @@ void grrt_destroy(GrrtCtx* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_cub_temp) cudaFree(ctx->d_cub_temp);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     delete ctx;
 }
 
@@ -940,6 +946,14 @@ __global__ void cost_keys_kernel(const uint32_t* sel, uint32_t n, const uint32_t
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = ~steps[sel[i]];   // ascending ~steps = descending steps; the radix sort is stable
 }
+// the pixels the second pass rewrote, packed for the read-back: [n] ids then [n][4] values
+__global__ void gather_pixels_kernel(const uint32_t* sel, uint32_t n, const double* xyza, double* packed) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* src = xyza + 4ull * sel[i];
+    double* dst = packed + 4ull * i;
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
 }  // namespace
 
 int grrt_order_by_cost_device(GrrtCtx* ctx, const uint32_t* d_selected, uint32_t n_selected, const uint32_t* d_steps,
@@ -1104,6 +1118,23 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
     CUDA_TRY(ctx, cudaEventRecord(ev[1], s));
     st.rays_base = n;
     const GrrtAdaptive& ad = ds->adaptive;
+    // Read-back overlapped with the second pass: when the caller's buffers are pinned, the base frame starts its way to the
+    // host now, on a second stream, and only the pixels the second pass rewrites follow afterwards (packed).  Pageable
+    // buffers would make the copy calls block this thread, so they take the plain path after the last pass.
+    bool early_copy = false;
+    if (ad.enabled || ad.show_sampling_mask) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, xyza_out) == cudaSuccess && pa.type == cudaMemoryTypeHost) early_copy = true;
+        cudaGetLastError();
+    }
+    if (early_copy) {
+        cudaStream_t cs = ctx->copy_stream;
+        CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ev[1], 0));
+        CUDA_TRY(ctx, cudaMemcpyAsync(xyza_out, xyza.p, n * 32, cudaMemcpyDeviceToHost, cs));
+        if (ray_class_out) CUDA_TRY(ctx, cudaMemcpyAsync(ray_class_out, cls.p, n, cudaMemcpyDeviceToHost, cs));
+        if (stop_reason_out) CUDA_TRY(ctx, cudaMemcpyAsync(stop_reason_out, stop.p, n, cudaMemcpyDeviceToHost, cs));
+        if (steps_out) CUDA_TRY(ctx, cudaMemcpyAsync(steps_out, steps.p, n * 4, cudaMemcpyDeviceToHost, cs));
+    }
     uint32_t n_sel = 0;
     CUDA_TRY(ctx, cudaEventRecord(ev[2], s));
     if (ad.enabled || ad.show_sampling_mask) {  // raytracer.rs:184
@@ -1166,10 +1197,33 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
         }
     }
     CUDA_TRY(ctx, cudaEventRecord(ev[3], s));
-    CUDA_TRY(ctx, cudaMemcpyAsync(xyza_out, xyza.p, n * 32, cudaMemcpyDeviceToHost, s));
-    if (ray_class_out) CUDA_TRY(ctx, cudaMemcpyAsync(ray_class_out, cls.p, n, cudaMemcpyDeviceToHost, s));
-    if (stop_reason_out) CUDA_TRY(ctx, cudaMemcpyAsync(stop_reason_out, stop.p, n, cudaMemcpyDeviceToHost, s));
-    if (steps_out) CUDA_TRY(ctx, cudaMemcpyAsync(steps_out, steps.p, n * 4, cudaMemcpyDeviceToHost, s));
+    DevBuf packed;
+    uint32_t n_patch = 0;
+    if (early_copy) {
+        n_patch = n_sel;   // the second pass (supersampling or mask colour) touched exactly the selected pixels
+        if (n_patch) {
+            const size_t need = (size_t)n_patch * (4 + 32);
+            if (need > ctx->h_stage_bytes) {
+                if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+                ctx->h_stage = nullptr;
+                ctx->h_stage_bytes = 0;
+                CUDA_TRY(ctx, cudaMallocHost(&ctx->h_stage, need + need / 4));
+                ctx->h_stage_bytes = need + need / 4;
+            }
+            CUDA_TRY(ctx, packed.alloc((size_t)n_patch * 32, s));
+            gather_pixels_kernel<<<(n_patch + 255) / 256, 256, 0, s>>>(sel.as<uint32_t>(), n_patch, xyza.as<double>(), packed.as<double>());
+            ++ctx->launches;
+            CUDA_TRY(ctx, cudaGetLastError());
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage, sel.p, (size_t)n_patch * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->h_stage + (((size_t)n_patch * 4 + 7) & ~(size_t)7), packed.p, (size_t)n_patch * 32,
+                                          cudaMemcpyDeviceToHost, s));
+        }
+    } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(xyza_out, xyza.p, n * 32, cudaMemcpyDeviceToHost, s));
+        if (ray_class_out) CUDA_TRY(ctx, cudaMemcpyAsync(ray_class_out, cls.p, n, cudaMemcpyDeviceToHost, s));
+        if (stop_reason_out) CUDA_TRY(ctx, cudaMemcpyAsync(stop_reason_out, stop.p, n, cudaMemcpyDeviceToHost, s));
+        if (steps_out) CUDA_TRY(ctx, cudaMemcpyAsync(steps_out, steps.p, n * 4, cudaMemcpyDeviceToHost, s));
+    }
     unsigned long long c[16], total[16];
     std::memset(total, 0, sizeof total);
     for (size_t d = 0; d < N; ++d) {   // the primary's stream has waited for every member's kernels
@@ -1181,6 +1235,12 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
     }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (early_copy) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));   // the base frame has landed; now the rewritten pixels on top
+        const uint32_t* ids = static_cast<const uint32_t*>(ctx->h_stage);
+        const double* vals = reinterpret_cast<const double*>((const char*)ctx->h_stage + (((size_t)n_patch * 4 + 7) & ~(size_t)7));
+        for (uint32_t i = 0; i < n_patch; ++i) std::memcpy(xyza_out + 4ull * ids[i], vals + 4ull * i, 32);
+    }
     st.attempts = total[CNT_ATTEMPTS];
     st.accepted_steps = total[CNT_ACCEPTED];
     st.raymarch_samples = total[CNT_SAMPLES];

@@ -111,3 +111,27 @@ def test_exact_build_is_tighter_and_fma_build_agrees(ctx, name):
     denom = np.maximum(np.abs(ora["xyza"][..., :3]).max(axis=-1), 1e-300)
     rel = np.abs(exact["xyza"][..., :3] - ora["xyza"][..., :3]).max(axis=-1) / denom
     assert np.quantile(rel[same], 0.99) < 1e-6
+
+
+def test_pinned_host_buffers_take_the_overlapped_read_back(ctx):
+    """With page-locked output buffers grrt_render copies the base frame out while the supersampling pass runs and then
+    patches the rewritten pixels; the frame must equal the one read back into pageable memory."""
+    import torch
+    for name, kw in (("C2", dict(width=96, height=64)), ("C1", dict(width=64, height=48))):
+        sc = oracle_config_scene(name, **kw)
+        want = ctx.render(sc)
+        assert want["stats"]["pixels_supersampled"] > 0
+        n = kw["width"] * kw["height"]
+        pinned = {"xyza": torch.zeros((n, 4), dtype=torch.float64).pin_memory().numpy(),
+                  "ray_class": torch.zeros(n, dtype=torch.uint8).pin_memory().numpy(),
+                  "stop": torch.zeros(n, dtype=torch.uint8).pin_memory().numpy(),
+                  "steps": torch.zeros(n, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+        for _ in range(2):
+            got = ctx.render(sc, out=pinned)
+            for key in ("xyza", "ray_class", "stop", "steps"):
+                assert np.array_equal(got[key], want[key]), (name, key)
+        crop = ctx.render(sc, 5, 7, 37, 61)
+        m = 32 * 54
+        sub = {k: v[:m] if k != "xyza" else v[:m] for k, v in pinned.items()}
+        got = ctx.render(sc, 5, 7, 37, 61, out=sub)
+        assert np.array_equal(got["xyza"], crop["xyza"]) and np.array_equal(got["steps"], crop["steps"])
