@@ -193,7 +193,7 @@ def scene_h2d_bytes(sc):
 
 # expected seconds of one full frame (base + adaptive pass) on ONE B200, measured in round 2 (profiles/r2_fullsize_*.json):
 # sizes the per-scene block so that the default run stays within minutes
-EXPECTED_S_1GPU = {"C1": 0.3, "C2": 0.25, "C3": 175.0, "C4": 350.0, "C5": 125.0}
+EXPECTED_S_1GPU = {"C1": 0.3, "C2": 0.22, "C3": 165.0, "C4": 350.0, "C5": 85.0}
 PER_SCENE_ORDER = ["C1", "C3", "C4", "C5"]
 
 
@@ -360,7 +360,8 @@ PARITY_RECORD = {
     "C3": "tests/test_gpu_fullsize.py::test_kerr_schild_configs_at_stated_size[C3] + profiles/r2_fullsize_C3.json: 300 of 300 sampled pixels "
           "(30 shadow rays > 1e5 steps) bit-equal step counts, XYZ within 1e-12",
     "C4": "tests/test_gpu_fullsize.py::test_kerr_schild_configs_at_stated_size[C4] + profiles/r2_fullsize_C4.json: 300 of 300 sampled pixels",
-    "C5": "profiles/r2_fullsize_C5_*.json (sampled pixels at 4096x4096 / 8192x8192) + tests/test_reference_image.py (Perlin pinned against the reference's own render)",
+    "C5": "profiles/r2_fullsize_C5_8192_1gpu.json / _8gpu_*.json: 300 of 300 sampled pixels of the 8192x8192 frame inside the gate with bit-equal step "
+          "counts (1 GPU and one 8-device context) + tests/test_reference_image.py (Perlin pinned against the reference's own render)",
 }
 
 
@@ -534,8 +535,11 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum of the base-pass launch and the FP64-pipe figure from the ncu --set full capture
 # of this command (C2 1500x1500, one GPU); see profiles/
 C2_NCU_RECORD = {
-    "traffic": 26.936320e6 + 75.075840e6,
-    "traffic_source": "profiles/r1_c2_trace_kernel_v12_1500.json (bytes per base-pass launch: the 85.5 MB of frame buffers written once, scene tables read once)",
+    "traffic": 27.091456e6 + 81.335808e6,
+    "traffic_source": "profiles/r2_c2_trace_kernel_inline_fallbacks_1500.json (ncu --set full, base-pass launch of this command: the 85.5 MB "
+                      "of frame buffers written once, scene tables read once)",
+    "fp64_pipe_busy_pct": 62.25,
+    "fp64_pipe_source": "profiles/r2_c2_trace_kernel_final_1500.json (sm__inst_executed_pipe_fp64, base-pass launch, 1500x1500)",
 }
 
 
