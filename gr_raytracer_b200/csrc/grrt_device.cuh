@@ -779,7 +779,8 @@ GD Cie texel_xyz(const DScene& S, const DTexture& t, uint32_t x, uint32_t y) {  
     double Z = (0.0193339 * r + 0.1191920 * g) + 0.9503041 * b;
     return cie(X, Y, Z, (double)px.w / 255.0);
 }
-GD Cie bitmap_bilinear(const DScene& S, const DTexture& t, double u, double v) {  // texture.rs:62-90
+// out of line: one copy for the celestial sphere and every object texture, and none inside the ray-march loop
+__device__ __noinline__ Cie bitmap_bilinear(const DScene& S, const DTexture& t, double u, double v) {  // texture.rs:62-90
     double p_x = (double)t.width * u;
     double p_y = (double)t.height * v;
     uint32_t xf = min(sat_u32(floor(p_x)), t.width - 1), yf = min(sat_u32(floor(p_y)), t.height - 1);

@@ -267,6 +267,14 @@ GD void init_ray(const DScene& S, const double pos[4], const double mom[4], doub
     F.pphi = inner_product<G>(S, pos, axial, mom);
 }
 
+// does_exit of a march without a cached exit distance (volumetric_disc.rs:154-170): four cylinder / cap intersections
+// per sample, out of line so that the march loop of the common (cached) case stays compact
+__device__ __noinline__ bool vol_does_exit_cold(const DObject& o, V3 p, V3 rd, double d_s) {
+    V3 to = v3(p.x + rd.x * d_s, p.y + rd.y * d_s, p.z + rd.z * d_s);
+    double t;
+    return vol_first_hit(o, p, to, t) && in01(t);
+}
+
 // ---- warp-cooperative VolumetricDisc ray-march (volumetric_disc.rs:209-328) --------------------------
 // Every argument is warp-uniform.  Returns the march colour; *err receives a GRRT_RAYERR_* when
 // compute_temperature failed (the caller turns that into (0,0,0,0) as color_at_uv does, :596-600).
@@ -370,9 +378,7 @@ __device__ __forceinline__ Cie vol_march_warp(const DScene& S, const DObject& o,
             if (cached) {
                 exited = d_o_next >= exit_distance;
             } else {  // does_exit (:154-170)
-                V3 to = v3(p.x + rd.x * d_s, p.y + rd.y * d_s, p.z + rd.z * d_s);
-                double t;
-                exited = vol_first_hit(o, p, to, t) && in01(t);
+                exited = vol_does_exit_cold(o, p, rd, d_s);
             }
         }
         const unsigned m_valid = __ballot_sync(kFull, valid);
