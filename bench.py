@@ -195,6 +195,8 @@ def scene_h2d_bytes(sc):
 # sizes the per-scene block so that the default run stays within minutes
 EXPECTED_S_1GPU = {"C1": 0.3, "C2": 0.22, "C3": 165.0, "C4": 350.0, "C5": 85.0}
 PER_SCENE_ORDER = ["C1", "C3", "C4", "C5"]
+FULL_FRAME_RECORD = {"C1": "tests/test_gpu_fullsize.py", "C3": "profiles/r2_fullsize_C3.json", "C4": "profiles/r2_fullsize_C4.json",
+                     "C5": "profiles/r2_fullsize_C5_8192_1gpu.json"}
 
 
 class Bench:
@@ -322,14 +324,14 @@ def per_scene_block(bench, budget_s):
                 rect, full = (0, 0, H, W // 2), False
             else:
                 out[name] = {"workload": wl["desc"], "skipped": f"time budget of the per-scene block used up ({budget_s:.0f} s); "
-                             f"a full frame takes about {EXPECTED_S_1GPU[name] / world:.0f} s on {world} GPU(s): profiles/r2_fullsize_{name}.json"}
+                             f"a full frame takes about {EXPECTED_S_1GPU[name] / world:.0f} s on {world} GPU(s): {FULL_FRAME_RECORD[name]}"}
                 continue
         elif expect > left:
             frac = (left - 3.0) / (EXPECTED_S_1GPU[name] / world * 1.5)   # the centre rows are the expensive ones
             rows = int(H * frac) // 4 * 4
             if rows < 16:
                 out[name] = {"workload": wl["desc"], "skipped": f"time budget of the per-scene block used up ({budget_s:.0f} s); "
-                             f"a full frame takes about {EXPECTED_S_1GPU[name] / world:.0f} s on {world} GPU(s): profiles/r2_fullsize_{name}.json"}
+                             f"a full frame takes about {EXPECTED_S_1GPU[name] / world:.0f} s on {world} GPU(s): {FULL_FRAME_RECORD[name]}"}
                 continue
             r0 = (H - rows) // 2
             rect, full = (r0, 0, r0 + rows, W), False
@@ -346,7 +348,7 @@ def per_scene_block(bench, budget_s):
             entry["section"] = {"from_row": rect[0], "to_row": rect[2], "from_col": rect[1], "to_col": rect[3],
                                 "note": "section of the full-size frame (the reference CLI's --from-row/--to-row/--from-col/--to-col): the left "
                                         "half for the Kerr-Schild scenes, a centred band of rows otherwise; the whole frame is recorded in "
-                                        "profiles/r2_fullsize_%s.json" % name}
+                                        "%s" % FULL_FRAME_RECORD[name]}
         out[name] = entry
         bench.close_frames(r)
     return out
