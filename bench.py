@@ -465,7 +465,9 @@ def main():
         st = out["stats"]
         e2e_rays = st["rays_base"] + st["rays_supersample"]
         d2h = W * H * (32 + 1 + 1 + 4) + 16 * 8 * world
-        e2e = {"value": e2e_rays / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": scene_h2d_bytes(sc) * world,
+        # one host -> device transfer of the scene per frame; the other devices of a multi-device context get the tables by
+        # peer copies from the first
+        e2e = {"value": e2e_rays / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": scene_h2d_bytes(sc),
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
                "api": "grrt_render (C ABI, host buffers)" if world == 1 else
                       f"grrt_render on one grrt_init_multi context over {world} GPUs (C ABI, host buffers, one process)"}

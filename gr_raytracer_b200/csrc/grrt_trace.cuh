@@ -7,23 +7,27 @@
 // (171 ... 15 500 ... 276 733) never idles a lane for long.
 //
 // Hot loop / events: the kernel is two nested loops.  The inner one runs RKF45 attempts until some
-// lane of the warp has an event (a chord hit an object, a ray ended, a lane is idle); everything
-// that handles events -- shading, the ray-march, terminal colour, write-out, ray set-up -- is
-// outside it, so the code executed thousands of times per ray is one contiguous ~1.5k
-// instructions.  Objects::intersects is split accordingly: its geometric half runs in the loop and
-// records which objects became the nearest hit at their turn; its shading half runs on the event,
-// in the same order, so that emitter errors fail the pixel exactly when the reference's `?` does.
+// lane of the warp has an event (an accepted step whose chord may touch an object or the celestial
+// sphere, a ray that ended, an idle lane); everything that handles events -- Cartesian end points and
+// the chord tests of Objects::intersects, the escape test, shading, the ray-march, terminal colour,
+// write-out, ray set-up -- is outside it.  Inside the loop an accepted step only runs the
+// conservative pre-filter segment_needs_cartesian() and the cheap stop tests.  Objects::intersects
+// is split accordingly: its geometric half records which objects became the nearest hit at their
+// turn; its shading half runs on them, in the same order, so that emitter errors fail the pixel
+// exactly when the reference's `?` does.
 //
-// RKF45 attempt: the six stages run as a real loop -- one copy of the right-hand side in the
-// instruction stream -- instead of six inlined copies (v1 was 12.6k instructions for KerrBL and
-// spent 1.4 stall cycles per issue waiting for instruction fetch,
-// profiles/r1_c2_trace_kernel_v1.json).  The stage derivatives k1..k5 live in shared memory
-// ([stage][component][thread], conflict-free), the 5th-order solution and the error vector are
-// accumulated in registers as each stage completes -- the same left-to-right order in which
-// runge_kutta.rs:115-123 sums them.  State components whose derivative is identically zero
-// (KerrBL: 6,7; Kerr-Schild: p_t; flat Cartesian: all momenta) are skipped: they contribute exact
-// zeros to every sum of the reference, so nothing changes numerically; and only the components the
-// right-hand side reads have their k stored.
+// RKF45 attempt: the stage derivatives k1..k5 live in shared memory ([stage][component][thread],
+// conflict-free).  State components whose derivative is identically zero (KerrBL: 6,7;
+// Kerr-Schild: p_t; flat Cartesian: all momenta) are skipped: they contribute exact zeros to every
+// sum of the reference, so nothing changes numerically; and only the components the right-hand
+// side reads have their k stored.  The exact build (-fmad=false; mandatory for the 2000-instruction
+// Kerr-Schild right-hand side) runs the six stages as a real loop -- one copy of the right-hand side
+// in the instruction stream -- and accumulates the 5th-order solution and the error vector as each
+// stage completes, in the order runge_kutta.rs:115-123 sums them.  The FMA build runs the stages as
+// straight-line code (GRRT_UNROLL_STAGES), takes sin / cos of a stage's polar angle from the state's
+// by the addition theorem (GRRT_SINCOS_DELTA) and forms y_new / the error vector of the stored
+// components at the last stage from the k1..k5 it loads anyway (GRRT_DEFER_SUMS).  The unrolled
+// KerrBL loop is instruction-fetch bound: rare paths inside it are calls.
 //
 // The reference stores the whole trajectory (112 B per step) and walks it a second time
 // (scene.rs:141-152); here each accepted step is tested against the objects as it is produced
