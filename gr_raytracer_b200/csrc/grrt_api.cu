@@ -1122,6 +1122,11 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
     // host now, on a second stream, and only the pixels the second pass rewrites follow afterwards (packed).  Pageable
     // buffers would make the copy calls block this thread, so they take the plain path after the last pass.
     bool early_copy = false;
+    struct CopyGuard {   // an early return must not leave copies into the caller's buffers in flight
+        cudaStream_t st;
+        const bool* started;
+        ~CopyGuard() { if (*started) cudaStreamSynchronize(st); }
+    } copy_guard{ctx->copy_stream, &early_copy};
     if (ad.enabled || ad.show_sampling_mask) {
         cudaPointerAttributes pa;
         if (cudaPointerGetAttributes(&pa, xyza_out) == cudaSuccess && pa.type == cudaMemoryTypeHost) early_copy = true;

@@ -94,3 +94,22 @@ def test_two_ranks_render_the_same_image_as_one(tmp_path):
     assert int(got["n_sel"]) == info["pixels_supersampled"]
     assert np.array_equal(got["xyza"], single.xyza.numpy())
     assert np.array_equal(got["cls"], single.cls.numpy()) and np.array_equal(got["stop"], single.stop.numpy())
+
+
+def test_section_render_and_cost_order_on_the_cpu_engine():
+    """FrameRenderer on a section (the reference's --from-row ... --to-col) equals the oracle's own section render, and
+    the cost order it derives is the stable descending-step-count order the device sort produces."""
+    sc = _scene()
+    rect = (4, 6, 24, 38)
+    fr = FrameRenderer(OracleEngine(sc), sc.c.adaptive, W, H, rect=rect)
+    info = fr.render()
+    ref = osc.render(sc, *rect)
+    assert np.array_equal(fr.xyza.numpy().reshape(20, 32, 4), ref["xyza"])
+    assert info["pixels_supersampled"] == ref["stats"]["pixels_supersampled"] > 0
+    n_sel = info["pixels_supersampled"]
+    sel = fr.selected[:n_sel].numpy().astype(np.int64)
+    order = fr.ordered[:n_sel].numpy().astype(np.int64)
+    steps = fr.steps.numpy().astype(np.int64)
+    assert np.array_equal(np.sort(order), sel)                               # a permutation of the flagged pixels
+    want = sel[np.argsort(-steps[sel], kind="stable")]                       # ties keep ascending pixel order
+    assert np.array_equal(order, want)
