@@ -1071,6 +1071,16 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
     }
     cudaStream_t s = ctx->stream;
     DevBuf xyza, cls, stop, steps, sel, ordered, cnt;
+    struct MembersIdle {   // destroyed before the buffers above: no member kernel may still store into a frame being freed
+        GrrtCtx* ctx;
+        ~MembersIdle() {
+            for (GrrtCtx* m : ctx->members) {
+                cudaSetDevice(m->device);
+                cudaStreamSynchronize(m->stream);
+            }
+            cudaSetDevice(ctx->device);
+        }
+    } members_idle{ctx};
     CUDA_TRY(ctx, xyza.alloc(n * 32, s));
     CUDA_TRY(ctx, cls.alloc(n, s));
     CUDA_TRY(ctx, stop.alloc(n, s));
