@@ -1,7 +1,7 @@
 """Renders one BASELINE.json configuration at its stated size through the C ABI and checks a sample of its pixels
 against the CPU oracle (test infrastructure; the render itself never touches it).
 
-    python tools/fullsize.py C3 [--samples 300] [--long 30] [--out gpurun_out/fullsize_C3.json] [--width W --height H]
+    python tests/fullsize_check.py C3 [--samples 300] [--long 30] [--out gpurun_out/fullsize_C3.json] [--width W --height H]
 
 The frame is the configuration as given (adaptive supersampling included).  Checked per sampled pixel:
  * step count of the 1-spp ray bit-equal to the oracle's, same stop reason;
@@ -19,7 +19,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # helpers.py
 
 import numpy as np  # noqa: E402
 

@@ -112,12 +112,10 @@ def test_full_frame_parity_gate(ctx, name):
 def test_kerr_schild_configs_at_stated_size(ctx, name):
     """C3 (1500x1500) and C4 (2048x2048) at --max-steps 1e6: the 1-spp pass of the whole frame on the device, 300 of its
     pixels -- 30 of them shadow rays with more than 1e5 accepted steps -- against the oracle with bit-equal step counts.
-    (The full frames with their 4x4 adaptive pass, 174 s and 346 s of one B200, are recorded by tools/fullsize.py in
+    (The full frames with their 4x4 adaptive pass, 174 s and 346 s of one B200, are recorded by tests/fullsize_check.py in
     profiles/r2_fullsize_C3.json / _C4.json with the same check.)"""
-    import sys
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import fullsize
-    res, dev = fullsize.run(name, 300, 30, ctx=ctx, adaptive=False)
+    import fullsize_check
+    res, dev = fullsize_check.run(name, 300, 30, ctx=ctx, adaptive=False)
     p = res["parity"]
     assert (res["height"], res["width"]) == (CONFIGS[name]["height"], CONFIGS[name]["width"])
     assert p["sampled"] == 300 and p["long_rays_sampled"] >= 30
