@@ -181,7 +181,7 @@ int main(int argc, char** argv) {
         else if (flag == "--position" || flag == "-p") at_pos = parse_list(value(i, flag), "--position");
         else if (flag == "--direction" || flag == "-d") at_dir = parse_list(value(i, flag), "--direction");
         else if (flag == "--camera-positions") positions_file = value(i, flag);
-        else if (flag == "--output-pattern") output_pattern = value(i, flag);
+        else if (flag == "--output-pattern") { output_pattern = value(i, flag); frame_file_name(output_pattern, 0); }  // validates
         else if (flag == "--first") first_frame = std::atoll(value(i, flag).c_str());
         else if (flag == "--stride") frame_stride = std::atoll(value(i, flag).c_str());
         else if (flag == "--count") frame_count = std::atoll(value(i, flag).c_str());
