@@ -16,8 +16,11 @@
 // is pinned against every known-answer value the reference's own unit tests hold for the
 // path (tests/test_oracle_kat.py).  The Perlin noise of VolumetricDisc
 // comes from the un-vendored crate `noise 0.9.0` (+ rand 0.8 / rand_xorshift 0.3); its
-// published algorithm is restated in `perlin_*` below and NO reference test pins a noise
-// value => "parity unpinned" for the Perlin density field (configs 4 and 5).
+// published algorithm is restated in `perlin_*` below.  No reference UNIT test pins a noise
+// value; the restatement is pinned instead against the image the reference binary itself
+// rendered with a frozen recipe (kerr_black_hole_with_stars.png, images/create-main-image.sh:
+// 40-79): tests/test_reference_image.py compares the oracle's render of that recipe with
+// crops of the image (a wrong permutation table fails it by a wide margin).
 //
 // Each function cites the reference file:line it follows.
 
