@@ -3,6 +3,7 @@
 // Compiled for sm_100a only (-gencode arch=compute_100a,code=sm_100a -fmad=false).  There is no CPU
 // path in this library: every entry point that computes needs a CUDA device and fails with
 // GRRT_ERR_CUDA otherwise.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -979,10 +980,11 @@ int grrt_order_by_cost_device(GrrtCtx* ctx, const uint32_t* d_selected, uint32_t
 
 namespace {
 // 8x4-pixel tiles dealt round-robin to the devices (tile-major, so 32 consecutive work units are one compact patch);
-// the same partition as gr_raytracer_b200/renderer.py:tile_interleaved_items
-int ensure_partition(GrrtCtx* ctx, uint32_t W, uint32_t H) {
+// the same partition as gr_raytracer_b200/renderer.py:tile_interleaved_items.  `order` (optional): the tiles in the
+// order they are to be dealt and traced (a pilot pass puts the expensive ones first); such a partition is not cached.
+int ensure_partition(GrrtCtx* ctx, uint32_t W, uint32_t H, const std::vector<uint32_t>* order = nullptr) {
     const size_t N = 1 + ctx->members.size();
-    if (ctx->part_w == W && ctx->part_h == H && ctx->d_part_items.size() == N) return GRRT_OK;
+    if (!order && ctx->part_w == W && ctx->part_h == H && ctx->d_part_items.size() == N) return GRRT_OK;
     for (size_t k = 0; k < ctx->d_part_items.size(); ++k) {
         if (!ctx->d_part_items[k]) continue;
         cudaSetDevice(k == 0 ? ctx->device : ctx->members[k - 1]->device);
@@ -991,14 +993,15 @@ int ensure_partition(GrrtCtx* ctx, uint32_t W, uint32_t H) {
     ctx->d_part_items.assign(N, nullptr);
     ctx->part_counts.assign(N, 0);
     ctx->part_w = ctx->part_h = 0;
-    const uint64_t tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4;
+    const uint64_t tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4, n_tiles = tiles_x * tiles_y;
     std::vector<uint32_t> ids;
     for (size_t d = 0; d < N; ++d) {
         ids.clear();
-        for (uint64_t t = d; t < tiles_x * tiles_y; t += N) {
+        for (uint64_t k = d; k < n_tiles; k += N) {
+            const uint64_t t = order ? (*order)[k] : k;
             const uint64_t ty = t / tiles_x, tx = t % tiles_x;
-            for (uint32_t k = 0; k < 32; ++k) {
-                const uint64_t py = ty * 4 + (k >> 3), px = tx * 8 + (k & 7);
+            for (uint32_t q = 0; q < 32; ++q) {
+                const uint64_t py = ty * 4 + (q >> 3), px = tx * 8 + (q & 7);
                 if (py < H && px < W) ids.push_back((uint32_t)(py * W + px));
             }
         }
@@ -1010,9 +1013,60 @@ int ensure_partition(GrrtCtx* ctx, uint32_t W, uint32_t H) {
             CUDA_TRY(ctx, cudaMemcpy(ctx->d_part_items[d], ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
         }
     }
-    ctx->part_w = W;
-    ctx->part_h = H;
+    if (!order) {
+        ctx->part_w = W;
+        ctx->part_h = H;
+    }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return GRRT_OK;
+}
+
+// ---- pilot pass (BASELINE.json north_star: "load-balanced from a pilot low-resolution pass") ---------------------------
+// Frames with a large step budget have a heavy tail: in config 3 (Kerr-Schild, --max-steps 1e6) 8 % of the rays crawl
+// towards the horizon for ~2.8e5 steps and 0.1 % use the whole budget, a serial chain of tens of seconds each.  Traced
+// in image order those rays start in the middle of the pass and the pass ends long after the queue is empty.  The pilot
+// traces the same section at 1/8 resolution with the step budget capped (a fraction of a per cent of the frame's work),
+// and the 8x4 tiles are then traced -- and dealt to the devices -- in descending pilot cost, so the long rays start
+// first.  The image does not depend on the order.
+constexpr uint64_t kPilotMinBudget = 65536;     // scenes with a smaller --max-steps have no tail worth a pilot
+constexpr uint64_t kPilotStepCap = 20000;
+constexpr uint32_t kPilotScale = 8;
+int pilot_tile_order(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_row, uint32_t from_col, uint32_t to_row, uint32_t to_col,
+                     std::vector<uint32_t>* order) {
+    const uint32_t W = to_col - from_col, H = to_row - from_row;
+    GrrtDeviceScene pilot = *ds;   // same tables, coarser camera, capped budget
+    DScene& p = pilot.s;
+    const double rows = std::ceil(ds->s.cam_rows / kPilotScale), cols = std::ceil(ds->s.cam_cols / kPilotScale);
+    p.cam_scale = ds->s.cam_scale * ds->s.cam_rows / rows;   // 2 tan(alpha/2) / rows (camera.rs:217-224)
+    p.cam_rows = rows;
+    p.cam_cols = cols;
+    p.max_steps = std::min<uint64_t>(ds->s.max_steps, kPilotStepCap);
+    const uint32_t fr = from_row / kPilotScale, fc = from_col / kPilotScale;
+    const uint32_t tr = (to_row + kPilotScale - 1) / kPilotScale, tc = (to_col + kPilotScale - 1) / kPilotScale;
+    const uint32_t PW = tc - fc, PH = tr - fr;
+    const size_t pn = (size_t)PW * PH;
+    cudaStream_t s = ctx->stream;
+    DevBuf xyza, steps;
+    CUDA_TRY(ctx, xyza.alloc(pn * 32, s));
+    CUDA_TRY(ctx, steps.alloc(pn * 4, s));
+    int rc = trace_items_impl(ctx, &pilot, nullptr, 0, pn, fr, fc, tr, tc, 0, xyza.as<double>(), nullptr, nullptr,
+                              steps.as<uint32_t>(), nullptr /* not counted in the frame's statistics */, s, TraceOpts());
+    if (rc) return rc;
+    std::vector<uint32_t> cost(pn);
+    CUDA_TRY(ctx, cudaMemcpyAsync(cost.data(), steps.p, pn * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    const uint32_t tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4;
+    std::vector<uint32_t> tile_cost((size_t)tiles_x * tiles_y);
+    for (uint32_t ty = 0; ty < tiles_y; ++ty)
+        for (uint32_t tx = 0; tx < tiles_x; ++tx) {
+            // the tile's first pixel in frame coordinates -> the pilot pixel that covers it
+            const uint32_t py = std::min((from_row + ty * 4) / kPilotScale - fr, PH - 1);
+            const uint32_t px = std::min((from_col + tx * 8) / kPilotScale - fc, PW - 1);
+            tile_cost[(size_t)ty * tiles_x + tx] = cost[(size_t)py * PW + px];
+        }
+    order->resize(tile_cost.size());
+    for (size_t k = 0; k < order->size(); ++k) (*order)[k] = (uint32_t)k;
+    std::stable_sort(order->begin(), order->end(), [&](uint32_t a, uint32_t b) { return tile_cost[a] > tile_cost[b]; });
     return GRRT_OK;
 }
 
@@ -1065,7 +1119,20 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
         int device;
         ~Restore() { cudaSetDevice(device); }
     } restore{ctx->device};
-    if (N > 1) {
+    // a pilot pass decides the tile order of frames with a heavy tail (GRRT_PILOT=0 switches it off)
+    const char* pilot_env = std::getenv("GRRT_PILOT");
+    const bool use_pilot = ds->s.max_steps > kPilotMinBudget && n >= 4096 && !(pilot_env && pilot_env[0] == '0');
+    EventSet events;
+    cudaEvent_t ev_pilot = nullptr;
+    if (use_pilot) {
+        CUDA_TRY(ctx, events.make(ctx->device, &ev_pilot));
+        CUDA_TRY(ctx, cudaEventRecord(ev_pilot, ctx->stream));
+        std::vector<uint32_t> order;
+        rc = pilot_tile_order(ctx, ds, from_row, from_col, to_row, to_col, &order);
+        if (rc) return rc;
+        rc = ensure_partition(ctx, W, H, &order);
+        if (rc) return rc;
+    } else if (N > 1) {
         rc = ensure_partition(ctx, W, H);
         if (rc) return rc;
     }
@@ -1091,12 +1158,11 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
         CUDA_TRY(ctx, cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
     }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    EventSet events;
     cudaEvent_t ev[4];
     for (auto& e : ev) CUDA_TRY(ctx, events.make(ctx->device, &e));
     CUDA_TRY(ctx, cudaEventRecord(ev[0], s));
     // ---- base pass ----
-    if (N == 1) {
+    if (N == 1 && !use_pilot) {
         rc = grrt_trace_items_device(ctx, ds, nullptr, 0, n, from_row, from_col, to_row, to_col, 0, xyza.as<double>(),
                                      cls.as<uint8_t>(), stop.as<uint8_t>(), steps.as<uint32_t>(),
                                      (uint64_t*)ctx->d_counters, s);
@@ -1267,6 +1333,11 @@ int grrt_render_resident(GrrtCtx* ctx, const GrrtDeviceScene* ds, uint32_t from_
     cudaEventElapsedTime(&ms, ev[1], ev[2]); st.device_ms_mask = ms;
     cudaEventElapsedTime(&ms, ev[2], ev[3]); st.device_ms_supersample = ms;
     cudaEventElapsedTime(&ms, ev[0], ev[3]); st.device_ms_total = ms;
+    if (use_pilot) {   // the pilot (its trace, the read-back of its step counts, the host-side tile sort) belongs to the base pass
+        cudaEventElapsedTime(&ms, ev_pilot, ev[0]);
+        st.device_ms_base += ms;
+        st.device_ms_total += ms;
+    }
     if (stats) *stats = st;
     return GRRT_OK;
 }
