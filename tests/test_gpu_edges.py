@@ -135,3 +135,33 @@ def test_pinned_host_buffers_take_the_overlapped_read_back(ctx):
         sub = {k: v[:m] if k != "xyza" else v[:m] for k, v in pinned.items()}
         got = ctx.render(sc, 5, 7, 37, 61, out=sub)
         assert np.array_equal(got["xyza"], crop["xyza"]) and np.array_equal(got["steps"], crop["steps"])
+
+
+def test_pilot_ordered_base_pass_is_bit_identical(ctx):
+    """Scenes with --max-steps above 65536 trace their tiles in the order of a 1/8-resolution pilot pass (and deal them
+    to the devices in that order); the frame, the step counts and the statistics must not change by a bit."""
+    import tomllib
+    with open(os.path.join(ROOT, CONFIGS["C3"]["toml"]), "rb") as f:
+        cfg = tomllib.load(f)
+    cfg["adaptive_sampling"] = {"enabled": False}
+    sc = osc.scene_from_config(cfg, config_opts("C3", width=96, height=64, max_steps=70000), ROOT)
+    old = os.environ.get("GRRT_PILOT")
+    try:
+        os.environ["GRRT_PILOT"] = "0"
+        plain = ctx.render(sc)
+        os.environ["GRRT_PILOT"] = "1"
+        piloted = ctx.render(sc)
+        crop_p = ctx.render(sc, 3, 5, 61, 93)          # a section large enough for the pilot (58 x 88 pixels)
+        os.environ["GRRT_PILOT"] = "0"
+        crop = ctx.render(sc, 3, 5, 61, 93)
+    finally:
+        if old is None:
+            os.environ.pop("GRRT_PILOT", None)
+        else:
+            os.environ["GRRT_PILOT"] = old
+    for key in ("xyza", "ray_class", "stop", "steps"):
+        assert np.array_equal(piloted[key], plain[key]), key
+        assert np.array_equal(crop_p[key], crop[key]), key
+    for key in ("accepted_steps", "attempts", "stop_histogram", "rays_base"):
+        assert piloted["stats"][key] == plain["stats"][key], key     # the pilot's own rays are not counted
+    assert piloted["steps"].max() > 20000                              # some rays outlive the pilot's budget cap
