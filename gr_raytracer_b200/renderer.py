@@ -4,14 +4,17 @@ for one GPU or for the ranks of a `torch.distributed` job.
 
 Multi-GPU (BASELINE.json north_star): pixels are independent, so the image is cut into 8x4-pixel
 tiles dealt round-robin to the ranks (fine-grained interleaving balances the spatially clustered
-shadow / disc work without a pilot pass).  The only coupling is the adaptive mask: it reads the 8
-neighbours of every pixel and a frame-global 99th-percentile luminance (raytracer.rs:118-129,
-386-458), so every rank needs the whole 1-spp base buffer (33 B per pixel); every rank then derives the
-same mask and supersamples its share of the flagged pixels.  No reduction is involved; the N-GPU image is
-bit-identical to the 1-GPU image.  The exchange is fused into the kernels: the ranks map each other's frame
-buffers (cudaIpc, NVLink peer access) and the trace kernel / the sub-sample mean kernel store every finished
-pixel into all of them, with a one-word all-reduce as the barrier between passes.  Where the buffers cannot be
-shared (or with GRRT_P2P=0) the same frame is assembled with NCCL all-gathers.
+shadow / disc work).  The only coupling is the adaptive mask: it reads the 8 neighbours of every
+pixel and a frame-global 99th-percentile luminance (raytracer.rs:118-129, 386-458), so every rank
+needs the whole 1-spp base buffer (37 B per pixel with the step counts); every rank then derives the
+same mask, orders the flagged pixels by descending base-pass step count (the base pass is the pilot
+of the second pass) and supersamples every world-th pixel of that list.  No reduction is involved;
+the N-GPU image is bit-identical to the 1-GPU image.  The exchange is fused into the kernels: the
+ranks map each other's frame buffers (cudaIpc, NVLink peer access) and the trace kernel / the
+sub-sample mean kernel store every finished pixel into all of them, with a one-word all-reduce as
+the barrier between passes and at the start of a frame.  Where the buffers cannot be shared (or with
+GRRT_P2P=0) the same frame is assembled with NCCL all-gathers.  (One process driving all GPUs --
+grrt_init_multi behind grrt_render -- is the C++ twin of this file, csrc/grrt_api.cu.)
 
 torch is plumbing here (device buffers, the current stream, the collective); the ray tracing, mask
 selection and tone mapping are the CUDA kernels of libgrrt.so reached through the C ABI.
