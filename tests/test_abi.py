@@ -58,3 +58,21 @@ def test_init_fails_loudly_without_a_device():
         assert e.code == abi.ERR_CUDA
     else:
         raise AssertionError("Context() must raise without a GPU")
+
+
+def test_header_is_plain_c99_and_a_c_consumer_links(tmp_path):
+    """include/grrt.h compiles as pedantic C99 and tests/c_abi_smoke.c links against libgrrt.so alone; without a GPU the
+    program assembles the scene on the host and then fails loudly at grrt_init (exit code 3): no CPU fallback."""
+    import subprocess
+    import torch
+    from helpers import ROOT
+    exe = str(tmp_path / "c_abi_smoke")
+    lib_dir = os.path.join(ROOT, "gr_raytracer_b200")
+    cc = subprocess.run(["cc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L", lib_dir, "-lgrrt", f"-Wl,-rpath,{lib_dir}"],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    if torch.cuda.is_available():
+        return   # the GPU run of the program is tests/test_gpu_cli.py::test_plain_c_consumer
+    r = subprocess.run([exe, os.path.join(ROOT, "scenes", "kerr-bl.toml"), ROOT, "16", "12", "1"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no usable CUDA device" in r.stderr
